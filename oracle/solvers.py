@@ -1,0 +1,135 @@
+"""CPU restatement of the shift-invert Arnoldi path (and dense QR-invert for small grids).
+
+Test infrastructure (see ``oracle/__init__.py``).  The reference delegates all
+arithmetic on this path to un-vendored, *unpinned* third-party libraries:
+BLAS/LAPACK (system ``liblapack-dev``, ``CMakeLists.txt:98-103``) and ARPACK
+(``arpack-ng`` git HEAD, ``.github/workflows/unit.yml:97-105``).  Here the same
+routines are taken from SciPy's bundled OpenBLAS (``zgbtrf/zgbtrs/zgbmv/zlarnv``)
+and SciPy's ARPACK (``znaupd/zneupd`` behind ``scipy.sparse.linalg.eigs``) and are
+driven exactly like the reference's call sites:
+
+  solve_arpack_shift_invert .. src/solvers/arnoldi/smod_arpack_shift_invert.f08:15-161
+  arpack_t defaults .......... src/solvers/arnoldi/mod_arpack_type.f08:74-102,194-275
+  band LU / solve ............ src/solvers/mod_linear_systems.f08:67-127
+  banded matvec .............. src/matrices/datastructure/mod_banded_operations.f08:18-41
+  QR-invert .................. src/solvers/smod_qr_invert.f08:46-135
+
+Parity of this file is pinned by the reference's own known answers
+(``tests/unit_tests/mod_test_solvers_arpack_shift_invert.pf:16-27``) and the
+``BASE_*_SI_*.dat`` baselines (see tests/test_oracle_solvers.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+import time
+
+import numpy as np
+import scipy
+import scipy.linalg
+from scipy.linalg import blas, lapack
+from scipy.sparse.linalg import ArpackNoConvergence, LinearOperator, eigs
+
+ZLARNV_SEED = (2022, 9, 30, 179)  # mod_arpack_type.f08:206
+
+
+def _openblas():
+    root = os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs")
+    libs = glob.glob(os.path.join(root, "libscipy_openblas*.so"))
+    if not libs:
+        raise OSError("scipy-bundled OpenBLAS not found")
+    return ctypes.CDLL(libs[0])
+
+
+def zlarnv(n: int, idist: int = 2, seed=ZLARNV_SEED) -> np.ndarray:
+    """LAPACK ``zlarnv`` (mod_arpack_type.f08:194-211): the Arnoldi start vector."""
+    lib = _openblas()
+    iseed = (ctypes.c_int * 4)(*seed)
+    out = np.empty(n, dtype=np.complex128)
+    lib.scipy_zlarnv_(ctypes.byref(ctypes.c_int(idist)), iseed, ctypes.byref(ctypes.c_int(n)),
+                      out.ctypes.data_as(ctypes.c_void_p))
+    return out
+
+
+def arpack_defaults(n, nev, ncv=0, maxiter=0, tol=0.0):
+    """ncv / maxiter / tol defaults (mod_arpack_type.f08:217-275,
+    src/settings/mod_solver_settings.f08:30-44)."""
+    if ncv == 0:
+        ncv = max(nev + 1, min(2 * nev, n))
+    if maxiter == 0:
+        maxiter = max(100, 10 * nev)
+    if tol == 0.0:
+        tol = 5.0e-15
+    return ncv, maxiter, tol
+
+
+class BandedLU:
+    """zgbtrf factors of a band matrix given in LAPACK (kl+ku+1, n) layout."""
+
+    def __init__(self, ab, kl, ku):
+        n = ab.shape[1]
+        lu_in = np.zeros((2 * kl + ku + 1, n), dtype=np.complex128, order="F")
+        lu_in[kl:, :] = ab   # mod_linear_systems.f08:114-121
+        self.kl, self.ku = kl, ku
+        self.lu, self.ipiv, self.info = lapack.zgbtrf(lu_in, kl, ku, overwrite_ab=True)
+
+    def solve(self, rhs):
+        x, info = lapack.zgbtrs(self.lu, self.kl, self.ku, rhs, self.ipiv)
+        return x
+
+
+def banded_matvec(ab, kl, ku, x):
+    n = ab.shape[1]
+    return blas.zgbmv(n, n, kl, ku, 1.0, ab, x)
+
+
+def shift_invert(A_band, B_band, kl, ku, sigma, nev, ncv=0, maxiter=0, tol=0.0, which="LM",
+                 v0=None, return_stats=False):
+    """Restatement of ``solve_arpack_shift_invert``.
+
+    Returns ``(omega, vr)``; with ``return_stats`` also a dict with n_op, timings and
+    the number of converged pairs (ARPACK info=1 "maxiter reached" is only a warning
+    in the reference, so non-converged runs return the converged subset).
+    """
+    n = A_band.shape[1]
+    ncv, maxiter, tol = arpack_defaults(n, nev, ncv, maxiter, tol)
+    if v0 is None:
+        v0 = zlarnv(n)
+    stats = {"n_op": 0, "t_matvec": 0.0, "t_solve": 0.0}
+    t0 = time.perf_counter()
+    lu = BandedLU(A_band - sigma * B_band, kl, ku)   # :56-59
+    stats["t_factor"] = time.perf_counter() - t0
+    stats["lu_info"] = int(lu.info)
+
+    def op(x):
+        t1 = time.perf_counter()
+        u = banded_matvec(B_band, kl, ku, x)   # :98
+        t2 = time.perf_counter()
+        y = lu.solve(u)                        # :99-104
+        t3 = time.perf_counter()
+        stats["n_op"] += 1
+        stats["t_matvec"] += t2 - t1
+        stats["t_solve"] += t3 - t2
+        return y
+
+    OP = LinearOperator((n, n), matvec=op, dtype=np.complex128)
+    t0 = time.perf_counter()
+    try:
+        nu, vr = eigs(OP, k=nev, which=which, ncv=ncv, maxiter=maxiter, tol=tol, v0=v0.copy())
+        nconv = nev
+    except ArpackNoConvergence as exc:
+        nu, vr = exc.eigenvalues, exc.eigenvectors
+        nconv = len(nu)
+    stats["t_iter"] = time.perf_counter() - t0
+    stats["nconv"] = nconv
+    omega = sigma + 1.0 / nu                   # :157
+    if return_stats:
+        return omega, vr, stats
+    return omega, vr
+
+
+def qr_invert(A_dense, B_dense):
+    """Dense B^-1 A then zgeev (smod_qr_invert.f08:46-135); small grids only."""
+    C = scipy.linalg.solve(B_dense, A_dense)
+    return scipy.linalg.eigvals(C)

@@ -1,0 +1,65 @@
+"""Extract golden vectors from the reference's own datfiles into small ``.npz`` fixtures.
+
+Run once in the build container (needs ``/root/reference``, which does not exist on
+the GPU box):  ``python tests/golden/make_golden.py``
+
+Sources (reference-owned data, never code):
+  tests/regression_tests/baseline/BASE_*.dat      (Legolas 1.2.1 regression baselines)
+  tests/pylbo_tests/utility_files/v2.0.0_mri_matrix.dat   (the only stored assembled A, B)
+Each fixture keeps: eigenvalues, base grid, Gaussian grid, the stored equilibrium
+arrays, parameters, units and (for the MRI file) the matrix triplets and the Gauss
+nodes/weights printed in its header.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.datfile import read_datfile  # noqa: E402
+
+REF = "/root/reference/tests"
+FILES = {
+    "uni_adiab_SI": "regression_tests/baseline/BASE_uni_adiab_SI_k2_0_k3_pi.dat",
+    "uni_adiab_QR": "regression_tests/baseline/BASE_uni_adiab_QR_k2_0_k3_pi.dat",
+    "suydam_QR": "regression_tests/baseline/BASE_suydam_QR_k2_1_k3_-1.2.dat",
+    "resistive_tearing_QR": "regression_tests/baseline/BASE_resistive_tearing_QR_k2_0.49_k3_0.dat",
+    "magnetothermal_SI": "regression_tests/baseline/BASE_magnetothermal_SI_k2_0_k3_1.dat",
+    "magnetothermal_QR": "regression_tests/baseline/BASE_magnetothermal_QR_k2_0_k3_1.dat",
+    "kh_cd_SI": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_SI_k2_-1_k3_pi.dat",
+    "kh_cd_QR": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_QR_k2_-1_k3_pi.dat",
+    "mri_matrix": "pylbo_tests/utility_files/v2.0.0_mri_matrix.dat",
+}
+
+
+def main():
+    for key, rel in FILES.items():
+        d = read_datfile(os.path.join(REF, rel))
+        out = {
+            "eigenvalues": d["eigenvalues"],
+            "grid": d["grid"],
+            "grid_gauss": d["grid_gauss"],
+            "meta": json.dumps({
+                "source": rel, "version": d["version"], "geometry": d["geometry"],
+                "gridpoints": d["gridpoints"], "gamma": d["gamma"], "eq_type": d["eq_type"],
+                "parameters": d["parameters"], "units": d["units"],
+            }),
+        }
+        for name, arr in d["equilibria"].items():
+            out["eq_" + name] = arr
+        if "gauss_nodes" in d:
+            out["gauss_nodes"] = d["gauss_nodes"]
+            out["gauss_weights"] = d["gauss_weights"]
+        if "matrix_A" in d:
+            out["A_rows"], out["A_cols"], out["A_vals"] = d["matrix_A"]
+            out["B_rows"], out["B_cols"], out["B_vals"] = d["matrix_B"]
+        path = os.path.join(HERE, key + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{key}: {os.path.getsize(path)} bytes")
+
+
+if __name__ == "__main__":
+    main()

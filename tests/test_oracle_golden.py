@@ -1,0 +1,241 @@
+"""Pin the CPU oracle against the reference's own golden data and known answers.
+
+Golden fixtures: tests/golden/*.npz (from the reference's datfiles, see make_golden.py).
+Known answers: tests/unit_tests/mod_test_splines.pf, mod_test_quadblock.pf,
+mod_test_boundaries.pf, mod_test_solvers_arpack_shift_invert.pf (reference tree).
+"""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import assembly as asm
+from oracle import equilibria as eq
+from oracle import solvers
+
+LEGACY = (asm.LEGACY_GAUSS_NODES, asm.LEGACY_GAUSS_WEIGHTS)
+
+
+def _legacy(eqf, gridpts=51, **kw):
+    s, grid, xg, fields = eqf(gridpts=gridpts, nodes=LEGACY[0], **kw)
+    s.gauss_nodes, s.gauss_weights = LEGACY
+    return s, grid, xg, fields
+
+
+# ---- mod_test_splines.pf:29-58
+def test_spline_known_answers():
+    one, two = np.array([1.0]), np.array([2.0])
+    got = np.ravel(asm.quadratic_factors(np.array([1.2]), one, two))
+    assert got == pytest.approx([0.64, 0.0, -0.12, 0.48], abs=1e-12)
+    got = np.ravel(asm.quadratic_factors_deriv(np.array([1.5]), one, two))
+    assert got == pytest.approx([0.0, 0.0, 1.0, -1.0], abs=1e-12)
+    got = np.ravel(asm.cubic_factors(np.array([1.7]), one, two))
+    assert got == pytest.approx([0.784, 0.216, -0.147, 0.063], abs=1e-12)
+    got = np.ravel(asm.cubic_factors_deriv(np.array([1.9]), one, two))
+    assert got == pytest.approx([0.54, -0.54, 0.63, -0.17], abs=1e-12)
+
+
+# ---- mod_test_quadblock.pf:25-62
+def test_quadblock_index_map():
+    sv = asm.STATE_VECTORS["mhd"]
+    el = asm.Elements(sv)
+    one = [np.ones(1)] * 4
+    spl = {"s": one}
+    el.add(np.array([3.0 + 1.0j]), "v3", "v2", "s", "s")
+    el.add(np.array([-1.0 + 5.0j]), "a2", "T", "s", "s")
+    quad = np.zeros((32, 32, 1), dtype=complex)
+    asm.add_to_quadblock(quad, el, 1.0, 16, spl)
+    quad = quad[:, :, 0]
+    rows1 = {7, 8, 23, 24}
+    cols1 = {5, 6, 21, 22}
+    rows2 = {13, 14, 29, 30}
+    cols2 = {9, 10, 25, 26}
+    for r in range(1, 33):
+        for c in range(1, 33):
+            if r in rows1 and c in cols1:
+                assert quad[r - 1, c - 1] == 3.0 + 1.0j
+            elif r in rows2 and c in cols2:
+                assert quad[r - 1, c - 1] == -1.0 + 5.0j
+            else:
+                assert quad[r - 1, c - 1] == 0.0
+
+
+# ---- mod_test_boundaries.pf (index sets quoted in SURVEY.md §4)
+def test_essential_boundary_indices():
+    s = asm.Settings(gridpts=10, k2=1.0, k3=2.5)
+    assert asm.essential_indices(s, "left") == [1, 5, 7, 9, 11, 3, 13, 15]
+    assert [i + 160 - 32 for i in asm.essential_indices(s, "right")] == [147, 157, 159]
+    s.perpendicular_conduction = True
+    assert asm.essential_indices(s, "left")[-1] == 10
+    assert asm.essential_indices(s, "right")[-1] + 128 == 154
+    s.perpendicular_conduction = False
+    s.viscosity = True
+    assert asm.essential_indices(s, "left")[-2:] == [6, 8]
+    assert [i + 128 for i in asm.essential_indices(s, "right")[-2:]] == [150, 152]
+    s.geometry = "cylindrical"
+    assert asm.essential_indices(s, "left") == [1, 5, 7, 9, 11, 3, 13, 15]
+    s = asm.Settings(gridpts=10, k2=0.0, k3=2.5, boundary_type="wall_weak")
+    assert asm.essential_indices(s, "left") == [1, 5, 7, 9, 11, 3, 13]
+
+
+# ---- tests/pylbo_tests/utility_files/v2.0.0_mri_matrix.dat: the stored assembled A and B
+def test_mri_matrix_triplets(golden):
+    g = golden("mri_matrix")
+    s, grid, xg, fields = eq.mri_accretion_eq(gridpts=5, nodes=g["gauss_nodes"])
+    s.gauss_nodes, s.gauss_weights = g["gauss_nodes"], g["gauss_weights"]
+    assert np.array_equal(grid, g["grid"])
+    assert np.abs(xg - g["grid_gauss"]).max() < 1e-15
+    A, B = asm.build_matrices(s, grid, xg, fields)
+    for M, key in ((A, "A"), (B, "B")):
+        r, c, v = M.to_coo()
+        # identical non-zero pattern AND identical insertion order
+        assert np.array_equal(r, g[key + "_rows"])
+        assert np.array_equal(c, g[key + "_cols"])
+        gv = g[key + "_vals"]
+        tol = 1e-12 * np.abs(gv) + 1e-15 * np.abs(gv).max()
+        assert np.all(np.abs(v - gv) <= tol)
+    # dense / band / matvec views agree
+    x = np.random.default_rng(0).standard_normal(80) + 0j
+    assert np.allclose(A.to_dense() @ x, A.matvec(x), rtol=1e-13, atol=1e-13)
+    assert np.allclose(solvers.banded_matvec(A.to_band(), 31, 31, x), A.matvec(x), atol=1e-12)
+
+
+EQ_PINS = [
+    ("uni_adiab_SI", eq.adiabatic_homo_eq, {}),
+    ("suydam_QR", eq.suydam_cluster_eq, {}),
+    ("resistive_tearing_QR", eq.resistive_tearing_eq, {}),
+    ("magnetothermal_SI", eq.magnetothermal_eq, {}),
+    ("kh_cd_SI", eq.kelvin_helmholtz_cd_eq, {}),
+]
+NAME_MAP = {"kappa_para": "tcpara", "kappa_perp": "tcperp", "grav": "g0", "Hall": "hallfactor",
+            "inertia": "inertiafactor"}
+
+
+@pytest.mark.parametrize("name,eqf,kw", EQ_PINS)
+def test_equilibrium_arrays_match_baselines(golden, name, eqf, kw):
+    g = golden(name)
+    s, grid, xg, fields = _legacy(eqf, **kw)
+    assert np.abs(grid - g["grid"]).max() < 5e-15
+    assert np.abs(xg - g["grid_gauss"]).max() < 5e-15
+    full = asm.complete_fields(fields, len(xg))
+    checked = 0
+    for key in g.files:
+        if not key.startswith("eq_"):
+            continue
+        mine = NAME_MAP.get(key[3:], key[3:])
+        if mine not in full:
+            continue   # B0 etc. are derived, not slots
+        ref = g[key]
+        assert np.abs(full[mine] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), key
+        checked += 1
+    assert checked >= 25
+
+
+def test_magnetothermal_units_and_conduction(golden):
+    g = golden("magnetothermal_SI")
+    meta = json.loads(str(g["meta"]))
+    u = eq.Units(unit_temperature=2.6e6, unit_magneticfield=10.0, unit_length=1.0e8,
+                 mean_molecular_weight=1.0)
+    for key in ("unit_time", "unit_density", "unit_velocity", "unit_numberdensity",
+                "unit_lambdaT", "unit_conduction", "unit_pressure"):
+        assert getattr(u, key) == pytest.approx(meta["units"][key], rel=1e-14)
+    # tests/regression_tests/test_magnetothermal_modes.py:45-48
+    assert eq.tcpara(np.array([1.0]), u)[0] == pytest.approx(1.98901013, abs=1e-8)
+
+
+SI_PINS = [
+    ("uni_adiab_SI", eq.adiabatic_homo_eq, 15.0 + 0j, 6, 0, 1e-11),
+    ("magnetothermal_SI", eq.magnetothermal_eq, 0.01 + 0.04j, 15, 0, 1e-7),
+    ("kh_cd_SI", eq.kelvin_helmholtz_cd_eq, 2.5 + 0.5j, 6, 300, 1e-10),
+]
+
+
+@pytest.mark.parametrize("name,eqf,sigma,nev,maxiter,tol", SI_PINS)
+def test_shift_invert_baselines(golden, name, eqf, sigma, nev, maxiter, tol):
+    g = golden(name)
+    s, grid, xg, fields = _legacy(eqf)
+    A, B = asm.build_matrices(s, grid, xg, fields)
+    omega, vr, st = solvers.shift_invert(A.to_band(), B.to_band(), 31, 31, sigma, nev,
+                                         maxiter=maxiter, return_stats=True)
+    assert st["nconv"] == nev
+    for w in g["eigenvalues"]:
+        assert np.min(np.abs(omega - w)) <= tol * abs(w)
+    # residual of the original pencil
+    for k in range(nev):
+        r = A.matvec(vr[:, k]) - omega[k] * B.matvec(vr[:, k])
+        assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(A.matvec(vr[:, k])) + 1e-10
+
+
+QR_PINS = [
+    ("kh_cd_QR", eq.kelvin_helmholtz_cd_eq, 0.3, 1e-11),
+    ("resistive_tearing_QR", eq.resistive_tearing_eq, 0.005, 1e-8),
+]
+
+
+@pytest.mark.parametrize("name,eqf,lo,tol", QR_PINS)
+def test_qr_invert_full_spectrum(golden, name, eqf, lo, tol):
+    g = golden(name)
+    s, grid, xg, fields = _legacy(eqf)
+    A, B = asm.build_matrices(s, grid, xg, fields)
+    w = solvers.qr_invert(A.to_dense(), B.to_dense())
+    gold = g["eigenvalues"]
+    sel = gold[(np.abs(gold) > lo) & (np.abs(gold) < 1e10)]
+    assert len(sel) > 500
+    assert max(np.min(np.abs(w - x)) / abs(x) for x in sel) <= tol
+    if name == "resistive_tearing_QR":   # the tearing mode itself
+        assert np.min(np.abs(w - 0.015020829511236034j)) < 1e-12
+
+
+# ---- tests/unit_tests/mod_test_solvers_arpack_shift_invert.pf:16-27,86-167
+EXPECTED_10 = np.array([
+    -0.7795557649951639 - 0.3190570519782475j, -0.40222728775310573 - 0.1591345610324656j,
+    0.19978864304130092 - 0.007120730856958498j, 0.2780763784935159 + 1.0564177001188444j,
+    0.49119510716997966 + 0.48905000276138166j, 0.5182657568800012 + 0.7479373467358982j,
+    0.707950211215408 + 0.8410713792802329j, 0.9836774139278549 + 0.46713965558429804j,
+    1.4744682873098567 + 1.7884905288463375j, 2.72570513179907 + 3.60539530105732j])
+
+
+def pencil_10():
+    a = np.zeros((10, 10), dtype=complex)
+    b = np.zeros((10, 10), dtype=complex)
+    for i in range(1, 11):
+        a[i - 1, i - 1] = (1.0 + 2.0j) * i
+        b[i - 1, i - 1] = (0.2 + 2.3j) * i
+    for i in range(1, 10):
+        a[i, i - 1] = (1.5 + 0.5j) * i
+        a[i - 1, i] = -2.0 * i + (3.0 + 5.0j)
+        b[i, i - 1] = 3.1 - 2.5j * i
+        b[i - 1, i] = (6.0 - 1.3j) * i
+    for i in range(1, 9):
+        a[i + 1, i - 1] = 1.0 - 2.5j * i
+        a[i - 1, i + 1] = (6.0 + 1.5j) * i
+    for i in range(1, 8):
+        a[i + 2, i - 1] = 0.3 + 1.8j * i
+    return a, b
+
+
+def dense_to_band(m, kl, ku):
+    n = m.shape[0]
+    ab = np.zeros((kl + ku + 1, n), dtype=complex)
+    for j in range(n):
+        for i in range(max(0, j - ku), min(n, j + kl + 1)):
+            ab[ku + i - j, j] = m[i, j]
+    return ab
+
+
+@pytest.mark.parametrize("sigma,idxs", [
+    (0.0 + 0.0j, [1, 2, 3, 5]), (1.0 + 0.0j, [3, 5, 6, 8]), (0.5j, [3, 4, 5, 6]),
+    (-1.0 + 0.2j, [1, 2, 3, 5]), (-0.5 - 0.35j, [1, 2, 3, 5]), (10.0 + 2.0j, [7, 8, 9, 10])])
+def test_shift_invert_pfunit_known_answers(sigma, idxs):
+    a, b = pencil_10()
+    omega, _ = solvers.shift_invert(dense_to_band(a, 3, 3), dense_to_band(b, 3, 3), 3, 3,
+                                    sigma, 4, maxiter=500)
+    omega = omega[np.argsort(omega.real)]
+    assert np.abs(omega - EXPECTED_10[np.array(idxs) - 1]).max() < 1e-12
+
+
+def test_zlarnv_is_deterministic_and_uniform():
+    v = solvers.zlarnv(1000)
+    assert np.array_equal(v, solvers.zlarnv(1000))
+    assert np.all(np.abs(v.real) < 1) and np.all(np.abs(v.imag) < 1)
+    assert abs(v.real.mean()) < 0.1
