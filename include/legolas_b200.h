@@ -1,0 +1,170 @@
+/* legolas_b200 — C ABI of the B200-native Legolas hot path.
+ *
+ * The reference (Legolas 2.0.6, pure Fortran) has no FFI for this path; the boundary
+ * is two Fortran call sites in `program legolas`:
+ *
+ *   call build_matrices(matrix_B, matrix_A, settings, grid, background, physics)
+ *        src/main.f08:68, src/matrices/mod_matrix_manager.f08:138-266
+ *   call solve_evp(matrix_A, matrix_B, settings, omega, right_eigenvectors)
+ *        src/main.f08:74 -> src/solvers/mod_solvers.f08:111-112
+ *        -> src/solvers/arnoldi/smod_arpack_main.f08:67-77
+ *        -> src/solvers/arnoldi/smod_arpack_shift_invert.f08:15-161
+ *
+ * A thin iso_c_binding shim (legolas_b200/fortran/) replaces those two
+ * bodies with calls into this library.  Conventions: all pointers are caller-owned HOST
+ * pointers unless a function name ends in `_device`; arrays are column-major;
+ * `complex(dp)` is two interleaved doubles (re, im); Fortran `logical` is int32_t;
+ * integers are int32_t; functions return 0 on success, a negative LGPU_E* code on an
+ * argument / runtime error (message via lgpu_last_error) and never call exit().
+ * A context is not re-entrant; different contexts may be used from different threads.
+ * There is NO CPU fallback: every entry point fails with LGPU_ENOGPU without a device.
+ */
+#ifndef LEGOLAS_B200_H
+#define LEGOLAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGPU_OK 0
+#define LGPU_EINVAL (-1)   /* invalid argument (logger%error in the reference)       */
+#define LGPU_ENOGPU (-2)   /* no CUDA device / CUDA runtime error                    */
+#define LGPU_ESTATE (-3)   /* call order violated (e.g. solve before assemble)       */
+#define LGPU_ENOMEM (-4)
+
+#define LGPU_N_FIELDS 38
+
+/* Slot order of the equilibrium / physics arrays sampled at grid%gaussian_grid.
+ * Each slot is 4*(gridpts-1) doubles; a NULL slot means "identically zero"
+ * (the reference's default `zero_func`, src/background/mod_background.f08:44-131). */
+enum lgpu_field {
+  LGPU_F_RHO0 = 0, LGPU_F_DRHO0, LGPU_F_T0, LGPU_F_DT0, LGPU_F_DDT0,
+  LGPU_F_B01, LGPU_F_B02, LGPU_F_DB02, LGPU_F_DDB02, LGPU_F_B03, LGPU_F_DB03, LGPU_F_DDB03,
+  LGPU_F_V01, LGPU_F_DV01, LGPU_F_DDV01, LGPU_F_V02, LGPU_F_DV02, LGPU_F_DDV02,
+  LGPU_F_V03, LGPU_F_DV03, LGPU_F_DDV03,
+  LGPU_F_G0, LGPU_F_ETA, LGPU_F_DETADT, LGPU_F_DETADR,
+  LGPU_F_L0, LGPU_F_DLDT, LGPU_F_DLDRHO,           /* heatloss%get_L0 / get_dLdT / get_dLdrho */
+  LGPU_F_TCPARA, LGPU_F_DTCPARADT, LGPU_F_TCPERP, LGPU_F_DTCPERPDRHO, LGPU_F_DTCPERPDT,
+  LGPU_F_DTCPERPDB2, LGPU_F_TCPREFACTOR, LGPU_F_DTCPREFACTORDR,
+  LGPU_F_HALLFACTOR, LGPU_F_INERTIAFACTOR
+};
+
+/* Scalars of settings_t / mod_equilibrium_params read by build_matrices and the
+ * boundary manager (src/boundaries/mod_boundary_manager.f08:87-107). */
+typedef struct {
+  int32_t gridpts;            /* settings%grid%get_gridpts()                              */
+  int32_t physics_type;       /* 0 "mhd" (8 eqs), 1 "hd" (5), 2 "hd-1d" (3)               */
+  int32_t geometry;           /* 0 Cartesian (eps=1, deps=0), 1 cylindrical (eps=x, deps=1)*/
+  int32_t incompressible;     /* gamma := 1e12, src/settings/mod_physics_settings.f08:90  */
+  int32_t flow, resistivity, cooling, heating, conduction, perpendicular_conduction;
+  int32_t viscosity, viscous_heating, hall, electron_inertia, gravity;
+  int32_t boundary_type;      /* 0 "wall", 1 "wall_weak"                                  */
+  int32_t coaxial;            /* settings%grid%coaxial                                    */
+  int32_t reserved;
+  double k2, k3;              /* mod_equilibrium_params                                   */
+  double gamma;               /* ratio of specific heats (ignored if incompressible)      */
+  double viscosity_value;     /* settings%physics%viscosity%get_viscosity_value()         */
+  double electron_fraction;   /* settings%physics%hall%get_electron_fraction()            */
+  double gauss_nodes[4];      /* mod_global_variables.f08:31-43; all zero = 2.0.6 values   */
+  double gauss_weights[4];
+} lgpu_settings;
+
+/* arpack_t after new_arpack_config (src/solvers/arnoldi/mod_arpack_type.f08:74-102):
+ * the host has already validated nev/ncv/which and resolved the ncv/maxiter/tol defaults. */
+typedef struct {
+  int32_t nev, ncv, maxiter;
+  char which[2];              /* "LM","SM","LR","SR","LI","SI"                            */
+  int16_t pad;
+  double tol;
+  double sigma_re, sigma_im;
+  int32_t refine_steps;       /* extra iterative-refinement sweeps per solve (default 0)  */
+  int32_t reserved;
+} lgpu_arnoldi;
+
+/* What the host copies back into arpack_cfg%info / iparam(5,9,10,11) so that
+ * parse_znaupd_info / parse_zneupd_info / parse_finished_stats work unchanged. */
+typedef struct {
+  int32_t info;               /* znaupd-style: 0 ok, 1 maxiter reached, 3 no shifts, -9 zero start vector */
+  int32_t nconv;              /* iparam(5)                                                */
+  int32_t n_op;               /* iparam(9)  OP*x applications                             */
+  int32_t n_bx;               /* iparam(10) (always 0: bmat = "I")                        */
+  int32_t n_reorth;           /* iparam(11) re-orthogonalisation passes                   */
+  int32_t n_restart;          /* iparam(3) on exit: Arnoldi update iterations taken       */
+  int32_t lu_info;            /* 0 or index (1-based block row) of a singular pivot block */
+  int32_t reserved;
+  double t_factor_ms, t_iter_ms, t_extract_ms;   /* device/host wall times of the phases  */
+} lgpu_stats;
+
+typedef struct lgpu_ctx lgpu_ctx;
+
+int lgpu_create(lgpu_ctx** ctx, int32_t device, int32_t log_level);
+int lgpu_destroy(lgpu_ctx* ctx);
+const char* lgpu_last_error(const lgpu_ctx* ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t); NULL = own stream. */
+int lgpu_set_stream(lgpu_ctx* ctx, void* cuda_stream);
+int lgpu_synchronize(lgpu_ctx* ctx);
+
+/* ---- replaces build_matrices (src/matrices/mod_matrix_manager.f08:138-266) -----------
+ * base_grid: gridpts doubles; gauss_grid: 4*(gridpts-1) doubles; fields: LGPU_N_FIELDS
+ * host pointers (NULL = zero).  A and B stay resident on the device in block-tridiagonal
+ * form.  `_device` variant: the same pointers are device pointers (inputs already in HBM). */
+int lgpu_assemble(lgpu_ctx* ctx, const lgpu_settings* settings, const double* base_grid,
+                  const double* gauss_grid, const double* const fields[LGPU_N_FIELDS]);
+int lgpu_assemble_device(lgpu_ctx* ctx, const lgpu_settings* settings, const double* base_grid,
+                         const double* gauss_grid, const double* const fields[LGPU_N_FIELDS]);
+
+/* matrix_t views of the device matrices (which: 0 = A, 1 = B).
+ * export_coo: triplets in the reference's output order (rows ascending, per-row insertion
+ * order; src/dataIO/mod_output.f08:476-508), 1-based; call with rows == NULL to get nnz.
+ * export_blocks: raw (gridpts, 3, d, d) complex blocks [sub, diag, super], each d x d block
+ * column-major, d = 2*nb_eqs.
+ * import_coo: load host-assembled matrices instead of lgpu_assemble (solve_evp on an
+ * arbitrary matrix_t pair whose half-bandwidth fits the block-tridiagonal envelope);
+ * n must be a multiple of 16. */
+int lgpu_matrix_dim(lgpu_ctx* ctx, int32_t* n);
+int lgpu_export_coo(lgpu_ctx* ctx, int32_t which, int64_t* nnz, int32_t* rows, int32_t* cols,
+                    double* vals_ri);
+int lgpu_export_blocks(lgpu_ctx* ctx, int32_t which, double* blocks_ri);
+int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const int32_t* rows,
+                    const int32_t* cols, const double* vals_ri);
+
+/* ---- pieces of solve_arpack_shift_invert, exposed for tests and other solvers ---------
+ * factorize: A - sigma*B -> block-cyclic-reduction factors (replaces zgbtrf,
+ *            src/solvers/mod_linear_systems.f08:102-127); lu_info as in lgpu_stats.
+ * solve:     x = (A - sigma*B)^-1 rhs   (replaces zgbtrs, mod_linear_systems.f08:67-97)
+ * matvec:    y = A*x or B*x             (replaces zgbmv, mod_banded_operations.f08:18-41)
+ * apply_op:  y = (A - sigma*B)^-1 B x   (one reverse-communication step, shift_invert :98-104) */
+int lgpu_factorize(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t* lu_info);
+int lgpu_solve(lgpu_ctx* ctx, const double* rhs_ri, double* x_ri, int32_t refine_steps);
+int lgpu_matvec(lgpu_ctx* ctx, int32_t which, const double* x_ri, double* y_ri);
+int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refine_steps);
+
+/* ---- replaces solve_arpack_shift_invert (smod_arpack_shift_invert.f08:15-161) ---------
+ * resid0_ri: start vector (N complex) = zlarnv(2, [2022,9,30,179], N) from the host
+ *            (mod_arpack_type.f08:194-211); omega_ri: nev complex, already back-transformed
+ *            omega = sigma + 1/nu (:157), entries nconv..nev-1 are NaN; vr_ri: N x nev complex,
+ *            ld = N, unit 2-norm Ritz vectors (may be NULL to skip the device->host copy). */
+int lgpu_shift_invert(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_ri,
+                      double* omega_ri, double* vr_ri, lgpu_stats* stats);
+/* Same, but the start vector is taken from / Ritz vectors are left in device memory
+ * (used for device-resident timing and for chaining into device-side consumers). */
+int lgpu_shift_invert_device(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_dev,
+                             double* omega_ri_host, double* vr_dev, lgpu_stats* stats);
+
+/* Host utility: LAPACK zlarnv(idist=2) (uniform (-1,1) re and im), bit-exact port of
+ * dlaruv's 48-bit multiplicative congruential generator; iseed[4] updated in place. */
+int lgpu_zlarnv(int32_t iseed[4], int32_t n, double* out_ri);
+
+/* Launch / traffic accounting since the last call (for bench.py's gpu_launches claim). */
+int lgpu_counters(lgpu_ctx* ctx, int64_t* kernel_launches, int32_t reset);
+/* Device time (ms, CUDA events on the context's stream) of the most recent
+ * assemble / factorize / arnoldi-loop / extraction phases. */
+int lgpu_phase_times(lgpu_ctx* ctx, double* t_assemble_ms, double* t_factor_ms,
+                     double* t_iter_ms, double* t_extract_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEGOLAS_B200_H */

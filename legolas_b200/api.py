@@ -1,0 +1,416 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+The reference host is Fortran (no compiler in this image), so the layer above the C ABI is
+mirrored here with the reference's names and argument meaning:
+
+  build_matrices(settings, grid, background, physics) ... src/matrices/mod_matrix_manager.f08:138-153
+  solve_evp(matrix_A, matrix_B, settings, omega, vr) ..... src/solvers/mod_solvers.f08:92-123
+  new_arpack_config(evpdim, mode, bmat, solver_settings) . src/solvers/arnoldi/mod_arpack_type.f08:74-102
+  solver defaults ........................................ src/settings/mod_solver_settings.f08:30-44
+
+All arithmetic happens in liblegolas_b200.so on the GPU (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import CArnoldi, CSettings, CStats, LgpuError, N_FIELDS
+
+FIELD_NAMES = (
+    "rho0", "drho0", "T0", "dT0", "ddT0",
+    "B01", "B02", "dB02", "ddB02", "B03", "dB03", "ddB03",
+    "v01", "dv01", "ddv01", "v02", "dv02", "ddv02", "v03", "dv03", "ddv03",
+    "g0", "eta", "detadT", "detadr", "L0", "dLdT", "dLdrho",
+    "tcpara", "dtcparadT", "tcperp", "dtcperpdrho", "dtcperpdT", "dtcperpdB2",
+    "tcprefactor", "dtcprefactordr", "hallfactor", "inertiafactor",
+)
+assert len(FIELD_NAMES) == N_FIELDS
+
+ZLARNV_SEED = (2022, 9, 30, 179)   # mod_arpack_type.f08:206
+PHYSICS_TYPES = {"mhd": 0, "hd": 1, "hd-1d": 2}
+GEOMETRIES = {"Cartesian": 0, "cylindrical": 1}
+BOUNDARY_TYPES = {"wall": 0, "wall_weak": 1}
+ALLOWED_WHICH = ("LM", "SM", "LR", "SR", "LI", "SI")
+
+
+class LegolasError(RuntimeError):
+    """logger%error in the reference (src/dataIO/mod_logging.f08:81-85) raises; so do we."""
+
+
+@dataclass
+class SolverSettings:
+    """solver_settings_t (src/settings/mod_solver_settings.f08:30-44)."""
+
+    solver: str = "QR-invert"
+    arpack_mode: str = "general"
+    number_of_eigenvalues: int = 10
+    which_eigenvalues: str = "LM"
+    maxiter: int = 0
+    ncv: int = 0
+    sigma: complex = complex(float("nan"), float("nan"))
+    tolerance: float = 5.0e-15
+    refine_steps: int = 0   # legolas_b200 extension: iterative-refinement sweeps per solve
+
+
+@dataclass
+class Settings:
+    """The part of settings_t (+ mod_equilibrium_params k2, k3) the hot path reads."""
+
+    gridpts: int = 51
+    geometry: str = "Cartesian"
+    physics_type: str = "mhd"
+    k2: float = 0.0
+    k3: float = 0.0
+    gamma: float = 5.0 / 3.0
+    incompressible: bool = False
+    flow: bool = False
+    resistivity: bool = False
+    cooling: bool = False
+    heating: bool = False
+    conduction: bool = False
+    perpendicular_conduction: bool = False
+    viscosity: bool = False
+    viscosity_value: float = 0.0
+    viscous_heating: bool = False
+    hall: bool = False
+    electron_inertia: bool = False
+    electron_fraction: float = 0.5
+    gravity: bool = False
+    boundary_type: str = "wall"
+    coaxial: bool = False
+    gauss_nodes: Optional[np.ndarray] = None     # None = Legolas 2.0.6 constants
+    gauss_weights: Optional[np.ndarray] = None
+    solvers: SolverSettings = field(default_factory=SolverSettings)
+
+    @property
+    def nb_eqs(self) -> int:
+        return {"mhd": 8, "hd": 5, "hd-1d": 3}[self.physics_type]
+
+    @property
+    def dim_matrix(self) -> int:     # src/settings/mod_dims.f08:36-44
+        return self.gridpts * 2 * self.nb_eqs
+
+    def to_c(self) -> CSettings:
+        if self.geometry not in GEOMETRIES:
+            raise LegolasError("geometry has no defined scale factor")
+        if self.boundary_type not in BOUNDARY_TYPES:
+            raise LegolasError(f"unknown boundary_type {self.boundary_type}")
+        if self.physics_type not in PHYSICS_TYPES:
+            raise LegolasError(f"unknown physics_type {self.physics_type}")
+        cs = CSettings()
+        cs.gridpts = self.gridpts
+        cs.physics_type = PHYSICS_TYPES[self.physics_type]
+        cs.geometry = GEOMETRIES[self.geometry]
+        for key in ("incompressible", "flow", "resistivity", "cooling", "heating", "conduction",
+                    "perpendicular_conduction", "viscosity", "viscous_heating", "hall",
+                    "electron_inertia", "gravity", "coaxial"):
+            setattr(cs, key, int(bool(getattr(self, key))))
+        cs.boundary_type = BOUNDARY_TYPES[self.boundary_type]
+        cs.k2, cs.k3, cs.gamma = self.k2, self.k3, self.gamma
+        cs.viscosity_value = self.viscosity_value
+        cs.electron_fraction = self.electron_fraction
+        if self.gauss_nodes is not None:
+            for i in range(4):
+                cs.gauss_nodes[i] = float(self.gauss_nodes[i])
+                cs.gauss_weights[i] = float(self.gauss_weights[i])
+        return cs
+
+
+@dataclass
+class ArpackConfig:
+    """arpack_t after new_arpack_config."""
+
+    evpdim: int
+    mode: int
+    bmat: str
+    nev: int
+    ncv: int
+    maxiter: int
+    which: str
+    tolerance: float
+    residual: np.ndarray
+    info: int = 1            # start vector supplied by us (mod_arpack_type.f08:210)
+    iparam: Dict[int, int] = field(default_factory=dict)
+
+
+def zlarnv(n: int, seed=ZLARNV_SEED) -> np.ndarray:
+    """LAPACK zlarnv(idist=2, iseed) — bit-exact (host utility of the library)."""
+    lib = _lib.load()
+    iseed = (C.c_int32 * 4)(*seed)
+    out = np.empty(n, dtype=np.complex128)
+    rc = lib.lgpu_zlarnv(iseed, n, out.ctypes.data)
+    if rc != 0:
+        raise LgpuError(rc, "lgpu_zlarnv")
+    return out
+
+
+def new_arpack_config(evpdim: int, mode: int, bmat: str, solver_settings: SolverSettings) -> ArpackConfig:
+    """Validation + defaults of mod_arpack_type.f08:74-275; writes the effective ncv /
+    maxiter back into ``solver_settings`` like the reference (:96-99)."""
+    if mode not in (1, 2, 3):
+        raise LegolasError(f"Arnoldi: mode = {mode} is invalid, expected 1, 2 or 3")
+    if bmat not in ("I", "G"):
+        raise LegolasError(f"Arnoldi: bmat = {bmat} is invalid, expected 'I' or 'G'")
+    which = solver_settings.which_eigenvalues
+    if which not in ALLOWED_WHICH:
+        raise LegolasError(f"Arnoldi: which_eigenvalues = {which} is invalid, expected one of "
+                           f"{list(ALLOWED_WHICH)}")
+    nev = solver_settings.number_of_eigenvalues
+    if nev <= 0:
+        raise LegolasError(f"Arnoldi: number of eigenvalues must be >= 0 but got {nev}")
+    if nev >= evpdim:
+        raise LegolasError(f"Arnoldi: number of eigenvalues ({nev}) >= matrix size ({evpdim})")
+    ncv = solver_settings.ncv
+    if ncv == 0:
+        ncv = max(nev + 1, min(2 * nev, evpdim))
+    if ncv - nev < 1:
+        raise LegolasError(f"ncv too low, expected ncv - nev >= 1 but got ncv - nev = {ncv - nev}")
+    if ncv > evpdim:
+        raise LegolasError(f"ncv too high, expected ncv < N but got ncv = {ncv} and N = {evpdim}")
+    maxiter = solver_settings.maxiter
+    if maxiter < 0:
+        raise LegolasError(f"Arnoldi: maxiter must be positive, but is equal to {maxiter}")
+    if maxiter == 0:
+        maxiter = max(100, 10 * nev)
+    solver_settings.maxiter = maxiter
+    solver_settings.ncv = ncv
+    cfg = ArpackConfig(evpdim=evpdim, mode=mode, bmat=bmat, nev=nev, ncv=ncv, maxiter=maxiter,
+                       which=which, tolerance=solver_settings.tolerance, residual=zlarnv(evpdim))
+    cfg.iparam = {1: 1, 3: maxiter, 7: mode}
+    return cfg
+
+
+class Context:
+    """Owns the device-resident A, B, the BCR factors and the Krylov basis (lgpu_ctx)."""
+
+    def __init__(self, device: int = 0, log_level: int = 0):
+        self._lib = _lib.load()
+        handle = C.c_void_p()
+        rc = self._lib.lgpu_create(C.byref(handle), device, log_level)
+        if rc != 0:
+            raise LgpuError(rc, "lgpu_create failed (no CUDA device? there is no CPU fallback)")
+        self._h = handle
+        self.device = device
+        self._keepalive = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.lgpu_last_error(self._h)
+            raise LgpuError(rc, f"{what}: {msg.decode() if msg else ''}")
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.lgpu_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def synchronize(self):
+        self._check(self._lib.lgpu_synchronize(self._h), "synchronize")
+
+    @property
+    def dim(self) -> int:
+        n = C.c_int32()
+        self._check(self._lib.lgpu_matrix_dim(self._h, C.byref(n)), "matrix_dim")
+        return n.value
+
+    def counters(self, reset: bool = False) -> int:
+        n = C.c_int64()
+        self._check(self._lib.lgpu_counters(self._h, C.byref(n), int(reset)), "counters")
+        return n.value
+
+    def phase_times(self) -> dict:
+        t = [C.c_double() for _ in range(4)]
+        self._check(self._lib.lgpu_phase_times(self._h, *[C.byref(x) for x in t]), "phase_times")
+        return dict(zip(("assemble_ms", "factor_ms", "iter_ms", "extract_ms"), (x.value for x in t)))
+
+    # ---- assembly
+    def assemble(self, settings: Settings, grid: np.ndarray, gauss_grid: np.ndarray,
+                 fields: Dict[str, np.ndarray]):
+        """Host arrays in, A and B resident on the device out."""
+        unknown = set(fields) - set(FIELD_NAMES)
+        if unknown:
+            raise LegolasError(f"unknown field(s) {sorted(unknown)}")
+        grid = np.ascontiguousarray(grid, dtype=np.float64)
+        gauss_grid = np.ascontiguousarray(gauss_grid, dtype=np.float64)
+        if grid.shape != (settings.gridpts,) or gauss_grid.shape != (4 * (settings.gridpts - 1),):
+            raise LegolasError("grid / gaussian grid size does not match settings%grid")
+        arrs, ptrs = [], (C.c_void_p * N_FIELDS)()
+        for i, name in enumerate(FIELD_NAMES):
+            val = fields.get(name)
+            if val is None:
+                ptrs[i] = None
+                continue
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(val, dtype=np.float64),
+                                                     gauss_grid.shape))
+            arrs.append(a)
+            ptrs[i] = a.ctypes.data
+        cs = settings.to_c()
+        self._check(self._lib.lgpu_assemble(self._h, C.byref(cs), grid.ctypes.data,
+                                            gauss_grid.ctypes.data, ptrs), "assemble")
+
+    def assemble_device(self, settings: Settings, grid_ptr: int, gauss_ptr: int, field_ptrs):
+        """Same with device pointers (inputs already resident in HBM)."""
+        ptrs = (C.c_void_p * N_FIELDS)()
+        for i in range(N_FIELDS):
+            ptrs[i] = field_ptrs[i] if field_ptrs[i] else None
+        cs = settings.to_c()
+        self._check(self._lib.lgpu_assemble_device(self._h, C.byref(cs), C.c_void_p(grid_ptr),
+                                                   C.c_void_p(gauss_ptr), ptrs), "assemble_device")
+
+    def export_blocks(self, which: str) -> np.ndarray:
+        """(gridpts, 3, 16, 16) complex: [sub, diag, super] blocks; [b, t, i, j] = row i, col j."""
+        n = self.dim
+        g = n // 16
+        raw = np.empty((g, 3, 16, 16), dtype=np.complex128)   # device blocks are column-major
+        self._check(self._lib.lgpu_export_blocks(self._h, _which(which), raw.ctypes.data),
+                    "export_blocks")
+        return np.ascontiguousarray(raw.transpose(0, 1, 3, 2))
+
+    def export_coo(self, which: str):
+        """Triplets (rows, cols, vals), 1-based, in the reference's datfile order."""
+        nnz = C.c_int64()
+        w = _which(which)
+        self._check(self._lib.lgpu_export_coo(self._h, w, C.byref(nnz), None, None, None), "export_coo")
+        rows = np.empty(nnz.value, dtype=np.int32)
+        cols = np.empty(nnz.value, dtype=np.int32)
+        vals = np.empty(nnz.value, dtype=np.complex128)
+        self._check(self._lib.lgpu_export_coo(self._h, w, C.byref(nnz), rows.ctypes.data,
+                                              cols.ctypes.data, vals.ctypes.data), "export_coo")
+        return rows, cols, vals
+
+    def import_coo(self, which: str, n: int, rows, cols, vals):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        vals = np.ascontiguousarray(vals, dtype=np.complex128)
+        self._check(self._lib.lgpu_import_coo(self._h, _which(which), n, len(rows), rows.ctypes.data,
+                                              cols.ctypes.data, vals.ctypes.data), "import_coo")
+
+    # ---- linear algebra pieces
+    def factorize(self, sigma: complex) -> int:
+        info = C.c_int32()
+        self._check(self._lib.lgpu_factorize(self._h, sigma.real, sigma.imag, C.byref(info)), "factorize")
+        return info.value
+
+    def _vec_call(self, fn, what, x, *extra):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        if x.shape != (self.dim,):
+            raise LegolasError(f"{what}: vector length {x.shape} != matrix dimension {self.dim}")
+        y = np.empty_like(x)
+        self._check(fn(self._h, *extra[:1], x.ctypes.data, y.ctypes.data, *extra[1:]), what)
+        return y
+
+    def solve(self, rhs, refine_steps: int = 0) -> np.ndarray:
+        rhs = np.ascontiguousarray(rhs, dtype=np.complex128)
+        x = np.empty_like(rhs)
+        self._check(self._lib.lgpu_solve(self._h, rhs.ctypes.data, x.ctypes.data, refine_steps), "solve")
+        return x
+
+    def matvec(self, which: str, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.empty_like(x)
+        self._check(self._lib.lgpu_matvec(self._h, _which(which), x.ctypes.data, y.ctypes.data), "matvec")
+        return y
+
+    def apply_op(self, x, refine_steps: int = 0) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        y = np.empty_like(x)
+        self._check(self._lib.lgpu_apply_op(self._h, x.ctypes.data, y.ctypes.data, refine_steps), "apply_op")
+        return y
+
+    # ---- the eigen-solve
+    def shift_invert(self, cfg: ArpackConfig, sigma: complex, refine_steps: int = 0,
+                     want_vectors: bool = True):
+        ca = _arnoldi_c(cfg, sigma, refine_steps)
+        resid = np.ascontiguousarray(cfg.residual, dtype=np.complex128)
+        omega = np.empty(cfg.nev, dtype=np.complex128)
+        vr = np.empty((cfg.evpdim, cfg.nev), dtype=np.complex128, order="F") if want_vectors else None
+        st = CStats()
+        self._check(self._lib.lgpu_shift_invert(
+            self._h, C.byref(ca), resid.ctypes.data, omega.ctypes.data,
+            vr.ctypes.data if vr is not None else None, C.byref(st)), "shift_invert")
+        return omega, vr, _stats_dict(st)
+
+    def shift_invert_device(self, cfg: ArpackConfig, sigma: complex, resid_ptr: int, vr_ptr: int,
+                            refine_steps: int = 0):
+        ca = _arnoldi_c(cfg, sigma, refine_steps)
+        omega = np.empty(cfg.nev, dtype=np.complex128)
+        st = CStats()
+        self._check(self._lib.lgpu_shift_invert_device(
+            self._h, C.byref(ca), C.c_void_p(resid_ptr), omega.ctypes.data,
+            C.c_void_p(vr_ptr) if vr_ptr else None, C.byref(st)), "shift_invert_device")
+        return omega, _stats_dict(st)
+
+
+def _which(which: str) -> int:
+    if which not in ("A", "B"):
+        raise LegolasError(f"invalid or empty matrix label: {which}")
+    return 0 if which == "A" else 1
+
+
+def _arnoldi_c(cfg: ArpackConfig, sigma: complex, refine_steps: int) -> CArnoldi:
+    ca = CArnoldi()
+    ca.nev, ca.ncv, ca.maxiter = cfg.nev, cfg.ncv, cfg.maxiter
+    ca.which = cfg.which.encode()
+    ca.tol = cfg.tolerance
+    ca.sigma_re, ca.sigma_im = sigma.real, sigma.imag
+    ca.refine_steps = refine_steps
+    return ca
+
+
+def _stats_dict(st: CStats) -> dict:
+    return {name: getattr(st, name) for name, _ in CStats._fields_ if name != "reserved"}
+
+
+# ------------------------------------------------------------------ reference-named entry points
+@dataclass
+class Matrices:
+    """Stand-in for the (matrix_A, matrix_B) pair of matrix_t: device-resident."""
+
+    ctx: Context
+    settings: Settings
+
+
+def build_matrices(settings: Settings, grid: np.ndarray, gauss_grid: np.ndarray,
+                   fields: Dict[str, np.ndarray], ctx: Optional[Context] = None) -> Matrices:
+    """``call build_matrices(matrix_B, matrix_A, settings, grid, background, physics)``.
+
+    ``fields`` are the background / physics procedure pointers sampled at ``grid%gaussian_grid``
+    (the Fortran shim samples them with ``from_function``); see ``FIELD_NAMES`` for the slots."""
+    ctx = ctx or Context()
+    ctx.assemble(settings, grid, gauss_grid, fields)
+    return Matrices(ctx=ctx, settings=settings)
+
+
+def solve_evp(matrices: Matrices, settings: Settings):
+    """``call solve_evp(matrix_A, matrix_B, settings, omega, right_eigenvectors)`` for
+    ``solver = "arnoldi"``, ``arpack_mode = "shift-invert"``.  Returns (omega, vr, arpack_cfg, stats);
+    omega(nconv:) is NaN when ARPACK-style convergence was not reached for all nev (a warning,
+    not an error, in the reference: mod_arpack_type.f08:375-381)."""
+    sv = settings.solvers
+    if sv.solver != "arnoldi":
+        raise LegolasError(f"solver {sv.solver!r} stays on the Fortran host; only 'arnoldi' is built here")
+    if sv.arpack_mode != "shift-invert":
+        raise LegolasError(f"arpack_mode {sv.arpack_mode!r} stays on the Fortran host; "
+                           "only 'shift-invert' is built here")
+    if math.isnan(sv.sigma.real) or math.isnan(sv.sigma.imag):
+        raise LegolasError("sigma is not set")
+    cfg = new_arpack_config(matrices.ctx.dim, mode=2, bmat="I", solver_settings=sv)
+    omega, vr, stats = matrices.ctx.shift_invert(cfg, complex(sv.sigma), sv.refine_steps)
+    cfg.info = stats["info"]
+    cfg.iparam.update({5: stats["nconv"], 9: stats["n_op"], 10: stats["n_bx"], 11: stats["n_reorth"]})
+    return omega, vr, cfg, stats

@@ -1,0 +1,787 @@
+// C ABI of liblegolas_b200 (include/legolas_b200.h): context, device buffers, and the CUDA
+// implementation of the KrylovOps used by the implicitly restarted Arnoldi driver.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/legolas_b200.h"
+#include "arnoldi.cuh"
+#include "assemble.cuh"
+#include "bcr.cuh"
+#include "common.cuh"
+#include "iram.hpp"
+
+using namespace lgpu;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  void ensure(size_t count) {
+    if (count <= cap) return;
+    release();
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    cap = count;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  void ensure(size_t count) {
+    if (count <= cap) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    CUDA_CHECK(cudaMallocHost(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    cap = count;
+  }
+};
+
+int env_int(const char* name, int fallback) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : fallback;
+}
+
+double now_ms() {
+  using clk = std::chrono::steady_clock;
+  return std::chrono::duration<double, std::milli>(clk::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct lgpu_ctx {
+  int device = 0;
+  int log_level = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // matrices
+  lgpu_settings settings{};
+  int G = 0;            // block rows (gridpts)
+  int N = 0;            // matrix dimension
+  bool have[2] = {false, false};
+  DevBuf<cd> A, B;
+  DevBuf<uint32_t> masks, natmasks;
+  DevBuf<double> d_grid, d_gauss, d_fields;
+  DevBuf<int32_t> d_plan_i32;
+  DevBuf<PairItem> d_items;
+
+  // factorisation
+  BcrPlan bplan;
+  DevBuf<cd> factors, fwork, rhs, delta, yvec;
+  DevBuf<int32_t> d_info;
+  bool factorized = false;
+  cd sigma{0.0, 0.0};
+  int lu_info = 0;
+
+  // vectors / Krylov storage
+  DevBuf<cd> vx, vy, vu, vr, ve;
+  DevBuf<cd> V, resid, Hdev, Qdev, Z, kpartial, khwork;
+  DevBuf<double> kscal;
+  DevBuf<unsigned int> kticket;
+  PinnedBuf<cd> h_stage;
+  PinnedBuf<double> h_scal;
+
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double t_assemble = 0, t_factor = 0, t_iter = 0, t_extract = 0;
+
+  bool assembled() const { return have[0] && have[1]; }
+  BcrDevice bdev() {
+    BcrDevice d{};
+    d.A = A.p; d.B = B.p; d.factors = factors.p; d.work = fwork.p; d.rhs = rhs.p;
+    d.delta = delta.p; d.yvec = yvec.p; d.info = d_info.p;
+    return d;
+  }
+};
+
+namespace {
+
+template <typename F>
+int guarded(lgpu_ctx* ctx, F&& body) {
+  if (!ctx) return LGPU_EINVAL;
+  try {
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    return body();
+  } catch (const CudaError& e) {
+    ctx->err = e.what();
+    return LGPU_ENOGPU;
+  } catch (const std::bad_alloc&) {
+    ctx->err = "host allocation failed";
+    return LGPU_ENOMEM;
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+    return LGPU_EINVAL;
+  }
+}
+
+int fail(lgpu_ctx* ctx, int code, const std::string& msg) {
+  ctx->err = msg;
+  return code;
+}
+
+void ensure_vectors(lgpu_ctx* c) {
+  const size_t n = static_cast<size_t>(c->N);
+  c->vx.ensure(n); c->vy.ensure(n); c->vu.ensure(n); c->vr.ensure(n); c->ve.ensure(n);
+}
+
+void ensure_krylov_work(lgpu_ctx* c) {
+  const size_t tiles = (static_cast<size_t>(c->N) + KRYLOV_TILE - 1) / KRYLOV_TILE;
+  c->kpartial.ensure(tiles * (KRYLOV_MAXCOL + 1));
+  c->khwork.ensure(KRYLOV_MAXCOL + 1);
+  if (!c->kscal.p) {
+    c->kscal.ensure(4);
+    c->kticket.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(c->kticket.p, 0, sizeof(unsigned int), c->stream));
+  }
+  c->h_scal.ensure(4);
+}
+
+KrylovWork kwork(lgpu_ctx* c) {
+  KrylovWork w{};
+  w.partial = c->kpartial.p; w.hwork = c->khwork.p; w.scal = c->kscal.p; w.ticket = c->kticket.p;
+  return w;
+}
+
+int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const double* d_gauss,
+                const FieldPtrs& fields) {
+  if (s->physics_type != 0)
+    return fail(c, LGPU_EINVAL, "only physics_type 0 (mhd, 8 equations) is built so far");
+  const int G = s->gridpts;
+  c->settings = *s;
+  c->G = G;
+  c->N = G * BLK;
+  c->factorized = false;
+  const size_t nblk = static_cast<size_t>(G) * 3 * BLK2;
+  c->A.ensure(nblk);
+  c->B.ensure(nblk);
+  c->masks.ensure(static_cast<size_t>(G) * MASK_WORDS);
+  c->natmasks.ensure(2 * 2 * 4 * 8 + 2);
+  CUDA_CHECK(cudaMemsetAsync(c->natmasks.p, 0, (2 * 2 * 4 * 8 + 2) * sizeof(uint32_t), c->stream));
+
+  AsmParams p{};
+  p.gridpts = G;
+  p.geometry = s->geometry;
+  p.k2 = s->k2; p.k3 = s->k3;
+  p.gamma_1 = (s->incompressible ? 1.0e12 : s->gamma) - 1.0;
+  p.mu = s->viscosity_value;
+  p.efrac = s->electron_fraction;
+  static const double nodes[4] = {-0.861136311594053, -0.339981043584856, 0.339981043584856,
+                                  0.861136311594053};
+  static const double weights[4] = {0.347854845137454, 0.652145154862546, 0.652145154862546,
+                                    0.347854845137454};
+  bool custom = false;
+  for (int i = 0; i < 4; ++i) custom = custom || s->gauss_weights[i] != 0.0;
+  for (int i = 0; i < 4; ++i) {
+    p.nodes[i] = custom ? s->gauss_nodes[i] : nodes[i];
+    p.weights[i] = custom ? s->gauss_weights[i] : weights[i];
+  }
+
+  // plans -> device
+  const TermPlan pe = build_term_plan(*s, false), pn = build_term_plan(*s, true);
+  const std::vector<int32_t> essl = essential_indices(*s, false), essr = essential_indices(*s, true);
+  std::vector<int32_t> packed;
+  auto push = [&](const std::vector<int32_t>& v) {
+    const size_t off = packed.size();
+    packed.insert(packed.end(), v.begin(), v.end());
+    return off;
+  };
+  const size_t o_sb_e = push(pe.slot_begin), o_t_e = push(pe.term_ids);
+  const size_t o_sb_n = push(pn.slot_begin), o_t_n = push(pn.term_ids);
+  const size_t o_el = push(essl), o_er = push(essr);
+  c->d_plan_i32.ensure(packed.size());
+  CUDA_CHECK(cudaMemcpyAsync(c->d_plan_i32.p, packed.data(), packed.size() * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->stream));
+  std::vector<PairItem> items = pe.items;
+  items.insert(items.end(), pn.items.begin(), pn.items.end());
+  c->d_items.ensure(items.size());
+  CUDA_CHECK(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(PairItem),
+                             cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));   // host vectors go out of scope below
+  DevicePlan de{pe.nslots(), static_cast<int32_t>(pe.items.size()), c->d_plan_i32.p + o_sb_e,
+                c->d_plan_i32.p + o_t_e, c->d_items.p};
+  DevicePlan dn{pn.nslots(), static_cast<int32_t>(pn.items.size()), c->d_plan_i32.p + o_sb_n,
+                c->d_plan_i32.p + o_t_n, c->d_items.p + pe.items.size()};
+
+  CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+  launch_assemble(p, de, fields, d_grid, d_gauss, c->A.p, c->B.p, c->masks.p, c->stream);
+  launch_boundaries(p, dn, fields, d_grid, d_gauss, c->A.p, c->B.p, c->masks.p, c->natmasks.p,
+                    c->d_plan_i32.p + o_el, static_cast<int>(essl.size()), c->d_plan_i32.p + o_er,
+                    static_cast<int>(essr.size()), c->stream);
+  c->launches += 2;
+  CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_CHECK(cudaEventSynchronize(c->ev1));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->t_assemble = ms;
+  c->have[0] = c->have[1] = true;
+  return LGPU_OK;
+}
+
+int do_factorize(lgpu_ctx* c, cd sigma) {
+  if (!c->assembled()) return fail(c, LGPU_ESTATE, "factorize: matrices not assembled");
+  if (c->bplan.n != c->G) {
+    c->bplan = make_bcr_plan(c->G, env_int("LGPU_BCR_M0", 5), env_int("LGPU_BCR_M1", 4),
+                             env_int("LGPU_BCR_TOP", 32));
+    c->factors.ensure(c->bplan.factor_blocks * BLK2);
+    c->fwork.ensure(c->bplan.work_blocks * BLK2);
+    c->rhs.ensure(c->bplan.rhs_vecs * BLK);
+    c->delta.ensure(c->bplan.delta_vecs * BLK);
+    c->yvec.ensure(static_cast<size_t>(c->N));
+    c->d_info.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(c->delta.p, 0, c->bplan.delta_vecs * BLK * sizeof(cd), c->stream));
+  }
+  ensure_vectors(c);
+  CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+  bcr_factorize(c->bplan, c->bdev(), sigma, c->stream, &c->launches);
+  CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+  int32_t info = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&info, c->d_info.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->t_factor = ms;
+  c->sigma = sigma;
+  c->lu_info = info;
+  c->factorized = true;
+  return LGPU_OK;
+}
+
+// x = M^-1 b on the device (b, x may alias), with optional iterative refinement
+void dev_solve(lgpu_ctx* c, const cd* b, cd* x, int refine) {
+  const cd* rhs = b;
+  if (refine > 0 && b == x) {   // refinement needs the original right-hand side
+    CUDA_CHECK(cudaMemcpyAsync(c->vr.p, b, sizeof(cd) * c->N, cudaMemcpyDeviceToDevice, c->stream));
+    rhs = c->vr.p;
+  }
+  bcr_solve(c->bplan, c->bdev(), rhs, x, c->stream, &c->launches);
+  for (int it = 0; it < refine; ++it) {
+    // e = M^-1 (b - (A - sigma B) x) ; x += e
+    block_matvec(c->G, c->A.p, c->B.p, cd{-1.0, 0.0}, c->sigma, x, rhs, c->ve.p, c->stream,
+                 &c->launches);
+    bcr_solve(c->bplan, c->bdev(), c->ve.p, c->ve.p, c->stream, &c->launches);
+    vec_axpby(c->N, cd{1.0, 0.0}, x, cd{1.0, 0.0}, c->ve.p, c->stream, &c->launches);
+  }
+}
+
+// y = M^-1 B x on the device (x, y may alias)
+void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
+  block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, c->vu.p, c->stream,
+               &c->launches);
+  dev_solve(c, c->vu.p, y, refine);
+}
+
+class CudaKrylovOps final : public KrylovOps {
+ public:
+  CudaKrylovOps(lgpu_ctx* c, int ncv, int refine) : c_(c), ncv_(ncv), refine_(refine) {}
+
+  void init_residual() override { dev_apply_op(c_, c_->resid.p, c_->resid.p, refine_); }
+
+  void extend(int k, int m) override {
+    const int n = c_->N;
+    const KrylovWork kw = kwork(c_);
+    cd* V = c_->V.p;
+    cd* H = c_->Hdev.p;
+    if (k == 0) krylov_norm(n, c_->resid.p, kw, c_->stream, &c_->launches);
+    for (int j = k; j < m; ++j) {
+      cd* vj = V + static_cast<size_t>(j) * n;
+      cd* hsub = j > 0 ? H + static_cast<size_t>(j - 1) * ncv_ + j : nullptr;
+      krylov_scale(n, c_->resid.p, vj, kw, hsub, c_->stream, &c_->launches);
+      dev_apply_op(c_, vj, c_->resid.p, refine_);
+      cd* hcol = H + static_cast<size_t>(j) * ncv_;
+      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->launches);
+      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->launches);
+      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->launches);
+      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->launches);
+    }
+  }
+
+  void fetch(int k, int m, cplx* H, int ldh, double* rnorm) override {
+    const size_t cnt = static_cast<size_t>(ncv_) * ncv_;
+    c_->h_stage.ensure(cnt);
+    CUDA_CHECK(cudaMemcpyAsync(c_->h_stage.p, c_->Hdev.p, cnt * sizeof(cd), cudaMemcpyDeviceToHost,
+                               c_->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c_->h_scal.p, c_->kscal.p, sizeof(double), cudaMemcpyDeviceToHost,
+                               c_->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c_->stream));
+    for (int j = k; j < m; ++j) {
+      for (int i = 0; i <= j; ++i) {
+        const cd v = c_->h_stage.p[static_cast<size_t>(j) * ncv_ + i];
+        H[static_cast<size_t>(j) * ldh + i] = cplx(v.x, v.y);
+      }
+      if (j > 0) {
+        const cd v = c_->h_stage.p[static_cast<size_t>(j - 1) * ncv_ + j];
+        H[static_cast<size_t>(j - 1) * ldh + j] = cplx(v.x, v.y);
+      }
+    }
+    *rnorm = c_->h_scal.p[0];
+  }
+
+  void upload_small(const cplx* M, int ld, int rows, int cols) {
+    const size_t cnt = static_cast<size_t>(ncv_) * ncv_;
+    c_->h_stage.ensure(cnt);
+    for (int j = 0; j < cols; ++j)
+      for (int i = 0; i < rows; ++i) {
+        const cplx v = M[static_cast<size_t>(j) * ld + i];
+        c_->h_stage.p[static_cast<size_t>(j) * ncv_ + i] = cd{v.real(), v.imag()};
+      }
+    CUDA_CHECK(cudaMemcpyAsync(c_->Qdev.p, c_->h_stage.p, cnt * sizeof(cd), cudaMemcpyHostToDevice,
+                               c_->stream));
+  }
+
+  void compress(int kplusp, int kev, const cplx* Q, int ldq, cplx sigmak, double betak) override {
+    const int n = c_->N;
+    upload_small(Q, ldq, kplusp, kev + 1 <= kplusp ? kev + 1 : kplusp);
+    const int nc = kev + 1 <= kplusp ? kev + 1 : kplusp;
+    basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nc, c_->V.p, n, c_->stream, &c_->launches);
+    vec_axpby(n, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
+              c_->V.p + static_cast<size_t>(kev) * n, c_->stream, &c_->launches);
+    krylov_norm(n, c_->resid.p, kwork(c_), c_->stream, &c_->launches);
+    // the staging buffer is reused by the next fetch(): make sure the upload has been consumed
+    CUDA_CHECK(cudaStreamSynchronize(c_->stream));
+  }
+
+  void ritz_vectors(int kplusp, int nconv, const cplx* S, int lds) override {
+    const int n = c_->N;
+    upload_small(S, lds, kplusp, nconv);
+    basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nconv, c_->Z.p, n, c_->stream,
+               &c_->launches);
+  }
+
+ private:
+  lgpu_ctx* c_;
+  int ncv_;
+  int refine_;
+};
+
+int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, bool resid_on_device,
+                    double* omega_ri, double* vr_out, bool vr_on_device, lgpu_stats* stats) {
+  if (!c->assembled()) return fail(c, LGPU_ESTATE, "shift_invert: matrices not assembled");
+  const int n = c->N;
+  if (cfg->nev <= 0 || cfg->nev >= n) return fail(c, LGPU_EINVAL, "nev out of range");
+  if (cfg->ncv - cfg->nev < 1 || cfg->ncv > n || cfg->ncv > KRYLOV_MAXCOL)
+    return fail(c, LGPU_EINVAL, "ncv out of range (nev + 1 <= ncv <= min(N, 128))");
+  if (cfg->maxiter <= 0) return fail(c, LGPU_EINVAL, "maxiter must be positive");
+  static const char* allowed[6] = {"LM", "SM", "LR", "SR", "LI", "SI"};
+  bool ok = false;
+  for (auto w : allowed) ok = ok || (w[0] == cfg->which[0] && w[1] == cfg->which[1]);
+  if (!ok) return fail(c, LGPU_EINVAL, "which must be one of LM SM LR SR LI SI");
+
+  int rc = do_factorize(c, cd{cfg->sigma_re, cfg->sigma_im});
+  if (rc != LGPU_OK) return rc;
+  const int ncv = cfg->ncv, nev = cfg->nev;
+  c->V.ensure(static_cast<size_t>(n) * ncv);
+  c->resid.ensure(n);
+  c->Hdev.ensure(static_cast<size_t>(ncv) * ncv);
+  c->Qdev.ensure(static_cast<size_t>(ncv) * ncv);
+  c->Z.ensure(static_cast<size_t>(n) * nev);
+  ensure_krylov_work(c);
+  CUDA_CHECK(cudaMemsetAsync(c->Hdev.p, 0, sizeof(cd) * ncv * ncv, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->resid.p, resid0, sizeof(cd) * n,
+                             resid_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             c->stream));
+
+  IramConfig ic;
+  ic.nev = nev; ic.ncv = ncv; ic.maxiter = cfg->maxiter; ic.tol = cfg->tol;
+  ic.which[0] = cfg->which[0]; ic.which[1] = cfg->which[1];
+  CudaKrylovOps ops(c, ncv, cfg->refine_steps);
+  Iram iram;
+  const double t0 = now_ms();
+  IramResult res = iram.run(ops, ic);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  const double t1 = now_ms();
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  for (int k = 0; k < nev; ++k) {
+    if (k < res.nconv) {
+      const cplx om = cplx(cfg->sigma_re, cfg->sigma_im) + 1.0 / res.ritz[k];   // :157
+      omega_ri[2 * k] = om.real();
+      omega_ri[2 * k + 1] = om.imag();
+    } else {
+      omega_ri[2 * k] = nan;
+      omega_ri[2 * k + 1] = nan;
+    }
+  }
+  if (vr_out) {
+    const size_t got = static_cast<size_t>(n) * res.nconv, all = static_cast<size_t>(n) * nev;
+    if (vr_on_device) {
+      CUDA_CHECK(cudaMemcpyAsync(vr_out, c->Z.p, got * sizeof(cd), cudaMemcpyDeviceToDevice, c->stream));
+      if (all > got)
+        CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<cd*>(vr_out) + got, 0, (all - got) * sizeof(cd),
+                                   c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(vr_out, c->Z.p, got * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (all > got) std::memset(vr_out + 2 * got, 0, (all - got) * sizeof(cd));
+    }
+  }
+  const double t2 = now_ms();
+  c->t_iter = t1 - t0;
+  c->t_extract = t2 - t1;
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->info = res.info;
+    stats->nconv = res.nconv;
+    stats->n_op = res.n_op;
+    stats->n_bx = 0;
+    stats->n_reorth = res.n_reorth;
+    stats->n_restart = res.n_iter;
+    stats->lu_info = c->lu_info;
+    stats->t_factor_ms = c->t_factor;
+    stats->t_iter_ms = c->t_iter;
+    stats->t_extract_ms = c->t_extract;
+  }
+  return LGPU_OK;
+}
+
+}  // namespace
+
+// ======================================================================= C entry points
+extern "C" {
+
+int lgpu_create(lgpu_ctx** out, int32_t device, int32_t log_level) {
+  if (!out) return LGPU_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+    return LGPU_ENOGPU;
+  std::unique_ptr<lgpu_ctx> c(new (std::nothrow) lgpu_ctx);
+  if (!c) return LGPU_ENOMEM;
+  c->device = device;
+  c->log_level = log_level;
+  if (cudaSetDevice(device) != cudaSuccess) return LGPU_ENOGPU;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return LGPU_ENOGPU;
+  c->own_stream = true;
+  if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
+    return LGPU_ENOGPU;
+  *out = c.release();
+  return LGPU_OK;
+}
+
+int lgpu_destroy(lgpu_ctx* ctx) {
+  if (!ctx) return LGPU_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  cudaStream_t own = ctx->own_stream ? ctx->stream : nullptr;
+  delete ctx;
+  if (own) cudaStreamDestroy(own);
+  return LGPU_OK;
+}
+
+const char* lgpu_last_error(const lgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int lgpu_set_stream(lgpu_ctx* ctx, void* cuda_stream) {
+  return guarded(ctx, [&] {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) {
+      if (cuda_stream == nullptr) return LGPU_OK;
+      cudaStreamDestroy(ctx->stream);
+      ctx->own_stream = false;
+    }
+    if (cuda_stream == nullptr) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    } else {
+      ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    }
+    return LGPU_OK;
+  });
+}
+
+int lgpu_synchronize(lgpu_ctx* ctx) {
+  return guarded(ctx, [&] {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LGPU_OK;
+  });
+}
+
+int lgpu_assemble(lgpu_ctx* ctx, const lgpu_settings* s, const double* base_grid,
+                  const double* gauss_grid, const double* const fields[LGPU_N_FIELDS]) {
+  return guarded(ctx, [&] {
+    if (!s || !base_grid || !gauss_grid || !fields) return fail(ctx, LGPU_EINVAL, "null argument");
+    if (s->gridpts < 2) return fail(ctx, LGPU_EINVAL, "gridpts must be >= 2");
+    const size_t G = s->gridpts, ng = 4 * (G - 1);
+    ctx->d_grid.ensure(G);
+    ctx->d_gauss.ensure(ng);
+    ctx->d_fields.ensure(ng * NFIELD);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_grid.p, base_grid, G * sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->d_gauss.p, gauss_grid, ng * sizeof(double),
+                               cudaMemcpyHostToDevice, ctx->stream));
+    FieldPtrs fp{};
+    for (int f = 0; f < NFIELD; ++f) {
+      if (!fields[f]) continue;
+      double* dst = ctx->d_fields.p + static_cast<size_t>(f) * ng;
+      CUDA_CHECK(cudaMemcpyAsync(dst, fields[f], ng * sizeof(double), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+      fp.f[f] = dst;
+    }
+    return do_assemble(ctx, s, ctx->d_grid.p, ctx->d_gauss.p, fp);
+  });
+}
+
+int lgpu_assemble_device(lgpu_ctx* ctx, const lgpu_settings* s, const double* base_grid,
+                         const double* gauss_grid, const double* const fields[LGPU_N_FIELDS]) {
+  return guarded(ctx, [&] {
+    if (!s || !base_grid || !gauss_grid || !fields) return fail(ctx, LGPU_EINVAL, "null argument");
+    if (s->gridpts < 2) return fail(ctx, LGPU_EINVAL, "gridpts must be >= 2");
+    FieldPtrs fp{};
+    for (int f = 0; f < NFIELD; ++f) fp.f[f] = fields[f];
+    return do_assemble(ctx, s, base_grid, gauss_grid, fp);
+  });
+}
+
+int lgpu_matrix_dim(lgpu_ctx* ctx, int32_t* n) {
+  if (!ctx || !n) return LGPU_EINVAL;
+  *n = ctx->N;
+  return LGPU_OK;
+}
+
+int lgpu_export_blocks(lgpu_ctx* ctx, int32_t which, double* blocks_ri) {
+  return guarded(ctx, [&] {
+    if (which < 0 || which > 1 || !blocks_ri) return fail(ctx, LGPU_EINVAL, "bad argument");
+    if (!ctx->have[which]) return fail(ctx, LGPU_ESTATE, "matrix not available");
+    const size_t cnt = static_cast<size_t>(ctx->G) * 3 * BLK2;
+    CUDA_CHECK(cudaMemcpyAsync(blocks_ri, which ? ctx->B.p : ctx->A.p, cnt * sizeof(cd),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LGPU_OK;
+  });
+}
+
+int lgpu_export_coo(lgpu_ctx* ctx, int32_t which, int64_t* nnz, int32_t* rows, int32_t* cols,
+                    double* vals_ri) {
+  return guarded(ctx, [&] {
+    if (which < 0 || which > 1 || !nnz) return fail(ctx, LGPU_EINVAL, "bad argument");
+    if (!ctx->have[which]) return fail(ctx, LGPU_ESTATE, "matrix not available");
+    const int G = ctx->G;
+    const size_t cnt = static_cast<size_t>(G) * 3 * BLK2;
+    std::vector<cd> blocks(cnt);
+    std::vector<uint32_t> masks(static_cast<size_t>(G) * MASK_WORDS), nat(2 * 2 * 4 * 8 + 2);
+    CUDA_CHECK(cudaMemcpyAsync(blocks.data(), which ? ctx->B.p : ctx->A.p, cnt * sizeof(cd),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(masks.data(), ctx->masks.p, masks.size() * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(nat.data(), ctx->natmasks.p, nat.size() * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    auto bit = [](const uint32_t* w, int idx) { return (w[idx >> 5] >> (idx & 31)) & 1u; };
+    int64_t count = 0;
+    const bool fill = rows && cols && vals_ri;
+    for (int b = 0; b < G; ++b) {
+      const uint32_t* mw = masks.data() + static_cast<size_t>(b) * MASK_WORDS + which * 32;
+      for (int i = 0; i < BLK; ++i) {
+        // per-row insertion order of the reference's linked list: element b-1 (sub, diag),
+        // element b (new diag entries, super), natural boundary, essential diagonal
+        int ent_tile[3 * BLK + 1], ent_col[3 * BLK + 1], ne = 0;
+        bool present[3][BLK] = {};
+        auto add = [&](int tile, int j) {
+          if (present[tile][j]) return;
+          present[tile][j] = true;
+          ent_tile[ne] = tile; ent_col[ne] = j; ++ne;
+        };
+        for (int j = 0; j < BLK; ++j) if (bit(mw + 0 * 8, j * BLK + i)) add(0, j);
+        for (int j = 0; j < BLK; ++j) if (bit(mw + 1 * 8, j * BLK + i)) add(1, j);
+        for (int j = 0; j < BLK; ++j) if (bit(mw + 2 * 8, j * BLK + i)) add(1, j);
+        for (int j = 0; j < BLK; ++j) if (bit(mw + 3 * 8, j * BLK + i)) add(2, j);
+        for (int edge = 0; edge < 2; ++edge) {
+          const int qr = edge == 0 ? b : b - (G - 2);
+          if (qr < 0 || qr > 1) continue;
+          for (int qc = 0; qc < 2; ++qc) {
+            const uint32_t* nw = nat.data() + ((edge * 2 + which) * 4 + qr * 2 + qc) * 8;
+            for (int j = 0; j < BLK; ++j)
+              if (bit(nw, j * BLK + i)) add(qc - qr + 1, j);
+          }
+          if (which == 1 && ((nat[2 * 2 * 4 * 8 + edge] >> (qr * BLK + i)) & 1u)) add(1, i);
+        }
+        for (int e = 0; e < ne; ++e) {
+          if (fill) {
+            const cd v = blocks[(static_cast<size_t>(b) * 3 + ent_tile[e]) * BLK2 + ent_col[e] * BLK + i];
+            rows[count] = b * BLK + i + 1;
+            cols[count] = (b + ent_tile[e] - 1) * BLK + ent_col[e] + 1;
+            vals_ri[2 * count] = v.x;
+            vals_ri[2 * count + 1] = v.y;
+          }
+          ++count;
+        }
+      }
+    }
+    *nnz = count;
+    return LGPU_OK;
+  });
+}
+
+int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const int32_t* rows,
+                    const int32_t* cols, const double* vals_ri) {
+  return guarded(ctx, [&] {
+    if (which < 0 || which > 1 || n <= 0 || n % BLK != 0 || nnz < 0)
+      return fail(ctx, LGPU_EINVAL, "import_coo: n must be a positive multiple of 16");
+    const int G = n / BLK;
+    if (ctx->have[1 - which] && ctx->G != G)
+      return fail(ctx, LGPU_EINVAL, "import_coo: A and B dimensions differ");
+    const size_t cnt = static_cast<size_t>(G) * 3 * BLK2;
+    std::vector<cd> blocks(cnt, cd{0.0, 0.0});
+    std::vector<uint32_t> masks(static_cast<size_t>(G) * MASK_WORDS, 0u);
+    if (ctx->have[1 - which] && ctx->masks.p) {
+      CUDA_CHECK(cudaMemcpy(masks.data(), ctx->masks.p, masks.size() * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost));
+      for (int b = 0; b < G; ++b)
+        for (int wd = 0; wd < 32; ++wd) masks[static_cast<size_t>(b) * MASK_WORDS + which * 32 + wd] = 0u;
+    }
+    for (int64_t k = 0; k < nnz; ++k) {
+      const int r = rows[k] - 1, c = cols[k] - 1;
+      if (r < 0 || r >= n || c < 0 || c >= n) return fail(ctx, LGPU_EINVAL, "import_coo: index out of range");
+      const int b = r / BLK, t = c / BLK - b + 1;
+      if (t < 0 || t > 2) return fail(ctx, LGPU_EINVAL, "import_coo: entry outside the block-tridiagonal envelope");
+      const int idx = (c % BLK) * BLK + r % BLK;
+      cd& dst = blocks[(static_cast<size_t>(b) * 3 + t) * BLK2 + idx];
+      dst.x += vals_ri[2 * k];
+      dst.y += vals_ri[2 * k + 1];
+      const int contrib = t == 0 ? 0 : (t == 1 ? 1 : 3);
+      masks[static_cast<size_t>(b) * MASK_WORDS + which * 32 + contrib * 8 + (idx >> 5)] |= 1u << (idx & 31);
+    }
+    ctx->G = G;
+    ctx->N = n;
+    ctx->factorized = false;
+    ctx->bplan.n = ctx->bplan.n == G ? G : 0;
+    (which ? ctx->B : ctx->A).ensure(cnt);
+    ctx->masks.ensure(masks.size());
+    ctx->natmasks.ensure(2 * 2 * 4 * 8 + 2);
+    CUDA_CHECK(cudaMemcpy((which ? ctx->B : ctx->A).p, blocks.data(), cnt * sizeof(cd), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(ctx->masks.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(ctx->natmasks.p, 0, (2 * 2 * 4 * 8 + 2) * sizeof(uint32_t)));
+    ctx->have[which] = true;
+    return LGPU_OK;
+  });
+}
+
+int lgpu_factorize(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t* lu_info) {
+  return guarded(ctx, [&] {
+    const int rc = do_factorize(ctx, cd{sigma_re, sigma_im});
+    if (rc == LGPU_OK && lu_info) *lu_info = ctx->lu_info;
+    return rc;
+  });
+}
+
+int lgpu_solve(lgpu_ctx* ctx, const double* rhs_ri, double* x_ri, int32_t refine_steps) {
+  return guarded(ctx, [&] {
+    if (!ctx->factorized) return fail(ctx, LGPU_ESTATE, "solve: call lgpu_factorize first");
+    if (!rhs_ri || !x_ri) return fail(ctx, LGPU_EINVAL, "null argument");
+    const size_t bytes = sizeof(cd) * ctx->N;
+    CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, rhs_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dev_solve(ctx, ctx->vx.p, ctx->vy.p, refine_steps);
+    CUDA_CHECK(cudaMemcpyAsync(x_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LGPU_OK;
+  });
+}
+
+int lgpu_matvec(lgpu_ctx* ctx, int32_t which, const double* x_ri, double* y_ri) {
+  return guarded(ctx, [&] {
+    if (which < 0 || which > 1 || !x_ri || !y_ri) return fail(ctx, LGPU_EINVAL, "bad argument");
+    if (!ctx->assembled()) return fail(ctx, LGPU_ESTATE, "matvec: matrices not assembled");
+    ensure_vectors(ctx);
+    const size_t bytes = sizeof(cd) * ctx->N;
+    CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, x_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    block_matvec(ctx->G, ctx->A.p, ctx->B.p, cd{which == 0 ? 1.0 : 0.0, 0.0},
+                 cd{which == 1 ? 1.0 : 0.0, 0.0}, ctx->vx.p, nullptr, ctx->vy.p, ctx->stream,
+                 &ctx->launches);
+    CUDA_CHECK(cudaMemcpyAsync(y_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LGPU_OK;
+  });
+}
+
+int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refine_steps) {
+  return guarded(ctx, [&] {
+    if (!ctx->factorized) return fail(ctx, LGPU_ESTATE, "apply_op: call lgpu_factorize first");
+    if (!x_ri || !y_ri) return fail(ctx, LGPU_EINVAL, "null argument");
+    const size_t bytes = sizeof(cd) * ctx->N;
+    CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, x_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dev_apply_op(ctx, ctx->vx.p, ctx->vy.p, refine_steps);
+    CUDA_CHECK(cudaMemcpyAsync(y_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return LGPU_OK;
+  });
+}
+
+int lgpu_shift_invert(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_ri,
+                      double* omega_ri, double* vr_ri, lgpu_stats* stats) {
+  return guarded(ctx, [&] {
+    if (!cfg || !resid0_ri || !omega_ri) return fail(ctx, LGPU_EINVAL, "null argument");
+    return do_shift_invert(ctx, cfg, resid0_ri, false, omega_ri, vr_ri, false, stats);
+  });
+}
+
+int lgpu_shift_invert_device(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_dev,
+                             double* omega_ri_host, double* vr_dev, lgpu_stats* stats) {
+  return guarded(ctx, [&] {
+    if (!cfg || !resid0_dev || !omega_ri_host) return fail(ctx, LGPU_EINVAL, "null argument");
+    return do_shift_invert(ctx, cfg, resid0_dev, true, omega_ri_host, vr_dev, true, stats);
+  });
+}
+
+int lgpu_zlarnv(int32_t iseed[4], int32_t n, double* out_ri) {
+  if (!iseed || n < 0 || (n > 0 && !out_ri)) return LGPU_EINVAL;
+  // LAPACK dlaruv: x_i = seed * a^i mod 2^48, a = 33952834046453, 128 numbers per call;
+  // zlarnv(idist = 2) draws 64 complex numbers per dlaruv call and maps u -> 2u - 1.
+  const uint64_t a = 33952834046453ull, mask = (1ull << 48) - 1;
+  uint64_t s = (static_cast<uint64_t>(iseed[0]) << 36) | (static_cast<uint64_t>(iseed[1]) << 24) |
+               (static_cast<uint64_t>(iseed[2]) << 12) | static_cast<uint64_t>(iseed[3]);
+  const int64_t total = 2 * static_cast<int64_t>(n);
+  const double scale = 1.0 / 281474976710656.0;   // 2^-48
+  for (int64_t pos = 0; pos < total;) {
+    const int64_t cnt = std::min<int64_t>(128, total - pos);
+    uint64_t m = 1;
+    for (int64_t i = 0; i < cnt; ++i) {
+      m = (m * a) & mask;
+      const uint64_t x = (s * m) & mask;
+      out_ri[pos + i] = 2.0 * (static_cast<double>(x) * scale) - 1.0;
+    }
+    s = (s * m) & mask;
+    pos += cnt;
+  }
+  iseed[0] = static_cast<int32_t>((s >> 36) & 4095);
+  iseed[1] = static_cast<int32_t>((s >> 24) & 4095);
+  iseed[2] = static_cast<int32_t>((s >> 12) & 4095);
+  iseed[3] = static_cast<int32_t>(s & 4095);
+  return LGPU_OK;
+}
+
+int lgpu_counters(lgpu_ctx* ctx, int64_t* kernel_launches, int32_t reset) {
+  if (!ctx) return LGPU_EINVAL;
+  if (kernel_launches) *kernel_launches = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return LGPU_OK;
+}
+
+int lgpu_phase_times(lgpu_ctx* ctx, double* t_assemble_ms, double* t_factor_ms, double* t_iter_ms,
+                     double* t_extract_ms) {
+  if (!ctx) return LGPU_EINVAL;
+  if (t_assemble_ms) *t_assemble_ms = ctx->t_assemble;
+  if (t_factor_ms) *t_factor_ms = ctx->t_factor;
+  if (t_iter_ms) *t_iter_ms = ctx->t_iter;
+  if (t_extract_ms) *t_extract_ms = ctx->t_extract;
+  return LGPU_OK;
+}
+
+}  // extern "C"

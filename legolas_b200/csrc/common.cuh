@@ -1,0 +1,80 @@
+// Shared helpers: complex128 value type with mixed real/complex operators, CUDA error
+// macros, and the device-side constants of the hot path.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace lgpu {
+
+// complex(dp): 16-byte aligned so a whole value moves with one 128-bit load/store.
+struct __align__(16) cd {
+  double x, y;
+};
+
+__host__ __device__ inline cd mk(double x, double y = 0.0) { return cd{x, y}; }
+__host__ __device__ inline cd operator+(cd a, cd b) { return cd{a.x + b.x, a.y + b.y}; }
+__host__ __device__ inline cd operator-(cd a, cd b) { return cd{a.x - b.x, a.y - b.y}; }
+__host__ __device__ inline cd operator-(cd a) { return cd{-a.x, -a.y}; }
+__host__ __device__ inline cd operator*(cd a, cd b) {
+  return cd{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+__host__ __device__ inline cd operator+(cd a, double b) { return cd{a.x + b, a.y}; }
+__host__ __device__ inline cd operator+(double a, cd b) { return cd{a + b.x, b.y}; }
+__host__ __device__ inline cd operator-(cd a, double b) { return cd{a.x - b, a.y}; }
+__host__ __device__ inline cd operator-(double a, cd b) { return cd{a - b.x, -b.y}; }
+__host__ __device__ inline cd operator*(cd a, double b) { return cd{a.x * b, a.y * b}; }
+__host__ __device__ inline cd operator*(double a, cd b) { return cd{a * b.x, a * b.y}; }
+__host__ __device__ inline cd operator/(cd a, double b) { return cd{a.x / b, a.y / b}; }
+__host__ __device__ inline cd& operator+=(cd& a, cd b) { a.x += b.x; a.y += b.y; return a; }
+__host__ __device__ inline cd& operator-=(cd& a, cd b) { a.x -= b.x; a.y -= b.y; return a; }
+__host__ __device__ inline cd conj(cd a) { return cd{a.x, -a.y}; }
+__host__ __device__ inline double abs2(cd a) { return a.x * a.x + a.y * a.y; }
+// a += b*c (4 FMAs)
+__host__ __device__ inline void cfma(cd& a, cd b, cd c) {
+  a.x = fma(b.x, c.x, a.x); a.x = fma(-b.y, c.y, a.x);
+  a.y = fma(b.x, c.y, a.y); a.y = fma(b.y, c.x, a.y);
+}
+// a -= b*c
+__host__ __device__ inline void cfms(cd& a, cd b, cd c) {
+  a.x = fma(-b.x, c.x, a.x); a.x = fma(b.y, c.y, a.x);
+  a.y = fma(-b.x, c.y, a.y); a.y = fma(-b.y, c.x, a.y);
+}
+// a += conj(b)*c
+__host__ __device__ inline void cfmac(cd& a, cd b, cd c) {
+  a.x = fma(b.x, c.x, a.x); a.x = fma(b.y, c.y, a.x);
+  a.y = fma(b.x, c.y, a.y); a.y = fma(-b.y, c.x, a.y);
+}
+// complex reciprocal (Smith's algorithm, like Fortran's complex division)
+__host__ __device__ inline cd crecip(cd a) {
+  if (fabs(a.x) >= fabs(a.y)) {
+    double r = a.y / a.x, den = a.x + a.y * r;
+    return cd{1.0 / den, -r / den};
+  }
+  double r = a.x / a.y, den = a.x * r + a.y;
+  return cd{r / den, -1.0 / den};
+}
+
+constexpr int BLK = 16;             // dim_subblock for MHD (src/settings/mod_dims.f08:36-44)
+constexpr int BLK2 = BLK * BLK;     // entries per block
+constexpr double DP_LIMIT = 5.0e-15;  // src/mod_global_variables.f08:19
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t err, const char* what, const char* file, int line) {
+  if (err != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(err));
+    throw CudaError(buf);
+  }
+}
+#define CUDA_CHECK(expr) ::lgpu::cuda_check((expr), #expr, __FILE__, __LINE__)
+
+}  // namespace lgpu

@@ -1,0 +1,248 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. Needs a B200."""
+import numpy as np
+import pytest
+
+import legolas_b200 as lb
+from legolas_b200 import equilibria as heq
+from oracle import assembly as asm
+from oracle import equilibria as oeq
+from oracle import solvers as osolvers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lb.Context()
+    yield c
+    c.close()
+
+
+def to_host_settings(so: asm.Settings) -> lb.Settings:
+    keys = ("gridpts", "geometry", "physics_type", "k2", "k3", "gamma", "incompressible", "flow",
+            "resistivity", "cooling", "heating", "conduction", "perpendicular_conduction",
+            "viscosity", "viscosity_value", "viscous_heating", "hall", "electron_inertia",
+            "electron_fraction", "gravity", "boundary_type", "coaxial")
+    s = lb.Settings(**{k: getattr(so, k) for k in keys})
+    s.gauss_nodes, s.gauss_weights = so.gauss_nodes, so.gauss_weights
+    return s
+
+
+def check_matrices(ctx, A, B):
+    """Element-wise |d| <= 1e-12 |ref| + 1e-15 max|ref| and bit-identical structure + order."""
+    for M, label in ((A, "A"), (B, "B")):
+        got = ctx.export_blocks(label)
+        ref = M.blocks
+        scale = np.abs(ref).max()
+        tol = 1e-12 * np.abs(ref) + 1e-15 * scale
+        bad = np.abs(got - ref) > tol
+        assert not bad.any(), (label, np.argwhere(bad)[:5], np.abs(got - ref).max())
+        r, c, v = ctx.export_coo(label)
+        ro, co, vo = M.to_coo()
+        assert len(r) == len(ro), (label, len(r), len(ro))
+        assert np.array_equal(r, ro) and np.array_equal(c, co), label
+        assert np.all(np.abs(v - vo) <= 1e-12 * np.abs(vo) + 1e-15 * scale)
+
+
+CONFIG_CASES = [
+    ("adiabatic_homo", 51, {}), ("suydam_cluster", 51, {}), ("resistive_tearing", 51, {}),
+    ("magnetothermal_instabilities", 51, {}), ("magnetothermal_instabilities", 51, {"k2": 10.0}),
+    ("kelvin_helmholtz_cd", 51, {}), ("MRI_accretion", 5, {}),
+    # ragged sizes around the 7-block-rows-per-CTA tiling and the smallest grids
+    ("kelvin_helmholtz_cd", 2, {}), ("kelvin_helmholtz_cd", 3, {}), ("resistive_tearing", 7, {}),
+    ("resistive_tearing", 8, {}), ("suydam_cluster", 14, {}), ("suydam_cluster", 15, {}),
+    ("magnetothermal_instabilities", 1001, {}),
+]
+
+
+@pytest.mark.parametrize("name,gridpts,kw", CONFIG_CASES)
+def test_assembly_matches_oracle(ctx, name, gridpts, kw):
+    s, grid, fields = heq.EQUILIBRIA[name](gridpts, **kw)
+    so, go, xgo, fo = oeq.EQUILIBRIA[name](gridpts=gridpts, **kw)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    ctx.assemble(s, grid.base_grid, grid.gaussian_grid, fields)
+    check_matrices(ctx, A, B)
+
+
+def test_assembly_replays_reference_golden_matrix(ctx, golden):
+    """tests/pylbo_tests/utility_files/v2.0.0_mri_matrix.dat, with its header's Gauss constants."""
+    g = golden("mri_matrix")
+    s, grid, fields = heq.mri_accretion(5)
+    s.gauss_nodes, s.gauss_weights = g["gauss_nodes"], g["gauss_weights"]
+    grid = heq.Grid(s, 1.0, 2.0, nodes=g["gauss_nodes"])
+    _, _, fields = heq.mri_accretion(5)   # fields must be sampled on the legacy Gaussian grid
+    so, go, xgo, fo = oeq.mri_accretion_eq(gridpts=5, nodes=g["gauss_nodes"])
+    ctx.assemble(s, grid.base_grid, grid.gaussian_grid, fo)
+    for label in ("A", "B"):
+        r, c, v = ctx.export_coo(label)
+        assert np.array_equal(r, g[label + "_rows"]) and np.array_equal(c, g[label + "_cols"])
+        gv = g[label + "_vals"]
+        assert np.all(np.abs(v - gv) <= 1e-12 * np.abs(gv) + 1e-15 * np.abs(g["A_vals"]).max())
+
+
+def random_case(seed, geometry, gridpts=23, **flags):
+    rng = np.random.default_rng(seed)
+    so = asm.Settings(gridpts=gridpts, geometry=geometry, k2=1.3, k3=-0.7, **flags)
+    start = 0.4 if geometry == "cylindrical" else -0.3
+    grid = np.sort(np.concatenate(([start], start + np.cumsum(rng.uniform(0.02, 0.08, gridpts - 1)))))
+    xg = asm.gaussian_grid(grid)
+    fields = {name: rng.uniform(0.3, 1.7, len(xg)) * rng.choice([-1.0, 1.0]) for name in asm.FIELD_NAMES}
+    fields["rho0"] = np.abs(fields["rho0"])
+    return so, grid, xg, fields
+
+
+ALL_ON = dict(flow=True, resistivity=True, cooling=True, heating=True, conduction=True,
+              perpendicular_conduction=True, viscosity=True, viscosity_value=0.37,
+              viscous_heating=True, hall=True, electron_inertia=True, electron_fraction=0.3,
+              gravity=True)
+
+
+@pytest.mark.parametrize("geometry", ["Cartesian", "cylindrical"])
+@pytest.mark.parametrize("flags", [
+    ALL_ON,
+    dict(ALL_ON, incompressible=True),
+    dict(ALL_ON, viscosity=False),                       # Hall A-terms vanish without viscosity
+    dict(ALL_ON, boundary_type="wall_weak", coaxial=True),
+    dict(flow=True, gravity=True),
+])
+def test_assembly_every_term_random_fields(ctx, geometry, flags):
+    """All 7 physics modules + all natural/essential boundary branches against the oracle on
+    random (non-physical) fields and a non-uniform grid: exercises every entry of terms.def."""
+    so, grid, xg, fields = random_case(7, geometry, **flags)
+    A, B = asm.build_matrices(so, grid, xg, fields)
+    ctx.assemble(to_host_settings(so), grid, xg, fields)
+    check_matrices(ctx, A, B)
+
+
+def test_matvec_and_solve_match_lapack(ctx):
+    rng = np.random.default_rng(3)
+    for name, gridpts, sigma in (("kelvin_helmholtz_cd", 51, 2.5 + 0.5j),
+                                 ("magnetothermal_instabilities", 333, 0.02 + 0.03j),
+                                 ("resistive_tearing", 1001, 0.3 - 0.2j),
+                                 ("adiabatic_homo", 2, 1.0 + 0.5j),
+                                 ("adiabatic_homo", 3, 1.0 + 0.5j),
+                                 ("suydam_cluster", 65, -0.13 + 0.005j)):
+        s, grid, fields = heq.EQUILIBRIA[name](gridpts)
+        so, go, xgo, fo = oeq.EQUILIBRIA[name](gridpts=gridpts)
+        A, B = asm.build_matrices(so, go, xgo, fo)
+        ctx.assemble(s, grid.base_grid, grid.gaussian_grid, fields)
+        n = A.n
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        for M, label in ((A, "A"), (B, "B")):
+            y, yo = ctx.matvec(label, x), M.matvec(x)
+            assert np.abs(y - yo).max() <= 1e-12 * np.abs(yo).max()
+        assert ctx.factorize(sigma) == 0
+        b = B.matvec(x)
+        Mm = asm.BlockTriMatrix(gridpts, 16, "M")
+        Mm.blocks = A.blocks - sigma * B.blocks
+        lu = osolvers.BandedLU(A.to_band() - sigma * B.to_band(), 31, 31)
+        xl = lu.solve(b)
+        nM = np.linalg.norm(Mm.blocks)
+
+        def bwd(v):
+            return np.linalg.norm(Mm.matvec(v) - b) / (nM * np.linalg.norm(v) + np.linalg.norm(b))
+
+        for refine in (0, 1):
+            xs = ctx.solve(b, refine_steps=refine)
+            assert np.all(np.isfinite(xs))
+            # backward error no worse than 1e3 x LAPACK's pivoted band LU (and tiny in absolute terms)
+            assert bwd(xs) <= max(1e3 * bwd(xl), 1e-15), (name, refine, bwd(xs), bwd(xl))
+        y = ctx.apply_op(x)
+        assert np.linalg.norm(y - ctx.solve(b)) <= 1e-12 * np.linalg.norm(y)
+
+
+def phase_normalise(v):
+    k = np.argmax(np.abs(v))
+    return v * (np.abs(v[k]) / v[k]) / np.linalg.norm(v)
+
+
+SI_CASES = [
+    ("adiabatic_homo", 51, 15.0 + 0j, 6, 0), ("kelvin_helmholtz_cd", 51, 2.5 + 0.5j, 6, 300),
+    ("magnetothermal_instabilities", 51, 0.01 + 0.04j, 15, 0),
+    ("resistive_tearing", 301, 0.3 - 0.2j, 20, 0),
+    ("magnetothermal_instabilities", 501, 0.02 + 0.03j, 20, 0),
+]
+
+
+@pytest.mark.parametrize("name,gridpts,sigma,nev,maxiter", SI_CASES)
+def test_shift_invert_matches_oracle(ctx, name, gridpts, sigma, nev, maxiter):
+    """Converged eigenvalues within 1e-8 relative of the reference-equivalent CPU path
+    (scipy LAPACK zgbtrf/zgbtrs + ARPACK), eigenvectors within 1e-6 after phase normalisation.
+    Where the CPU path's own pencil residual is above 1e-9 (ill-conditioned members of
+    accumulation sequences) the tolerance follows that residual."""
+    s, grid, fields = heq.EQUILIBRIA[name](gridpts)
+    so, go, xgo, fo = oeq.EQUILIBRIA[name](gridpts=gridpts)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert",
+                                  number_of_eigenvalues=nev, sigma=sigma, maxiter=maxiter)
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    omega, vr, cfg, stats = lb.solve_evp(mats, s)
+    om_o, vr_o, st_o = osolvers.shift_invert(A.to_band(), B.to_band(), 31, 31, sigma, nev,
+                                             maxiter=maxiter, return_stats=True)
+    assert stats["nconv"] == st_o["nconv"] == nev
+    assert stats["info"] == 0 and stats["lu_info"] == 0
+    assert abs(stats["n_op"] - st_o["n_op"]) <= 0.25 * st_o["n_op"] + 2 * cfg.ncv
+
+    def rel_res(w, v):
+        bv = B.matvec(v)
+        return np.linalg.norm(A.matvec(v) - w * bv) / np.linalg.norm(w * bv)
+
+    for k in range(nev):
+        j = int(np.argmin(np.abs(om_o - omega[k])))
+        res_o, res_g = rel_res(om_o[j], vr_o[:, j]), rel_res(omega[k], vr[:, k])
+        tol = max(1e-8, 50.0 * res_o)
+        assert abs(omega[k] - om_o[j]) <= tol * abs(om_o[j]), (k, omega[k], om_o[j], res_o)
+        assert res_g <= max(10.0 * res_o, 1e-9), (k, res_g, res_o)
+        assert abs(np.linalg.norm(vr[:, k]) - 1.0) < 1e-10
+        if res_o < 1e-10:
+            d = np.linalg.norm(phase_normalise(vr[:, k]) - phase_normalise(vr_o[:, j]))
+            assert d <= 1e-6, (k, d)
+
+
+def test_adiabatic_shift_invert_golden_baseline(ctx, golden):
+    """BASE_uni_adiab_SI_k2_0_k3_pi.dat: the reference's own stored shift-invert eigenvalues."""
+    g = golden("uni_adiab_SI")
+    s, grid, fields = heq.adiabatic_homo(51)
+    s.gauss_nodes, s.gauss_weights = asm.LEGACY_GAUSS_NODES, asm.LEGACY_GAUSS_WEIGHTS
+    grid = heq.Grid(s, 0.0, 1.0, nodes=asm.LEGACY_GAUSS_NODES)
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert",
+                                  number_of_eigenvalues=6, sigma=15.0 + 0j)
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    omega, _, _, stats = lb.solve_evp(mats, s)
+    assert stats["nconv"] == 6
+    for w in g["eigenvalues"]:
+        assert np.min(np.abs(omega - w)) <= 1e-10 * abs(w)
+
+
+# ---- tests/unit_tests/mod_test_solvers_arpack_shift_invert.pf (10 x 10 pencil, 6 shifts)
+@pytest.mark.parametrize("sigma,idxs", [
+    (0.0 + 0.0j, [1, 2, 3, 5]), (1.0 + 0.0j, [3, 5, 6, 8]), (0.5j, [3, 4, 5, 6]),
+    (-1.0 + 0.2j, [1, 2, 3, 5]), (-0.5 - 0.35j, [1, 2, 3, 5]), (10.0 + 2.0j, [7, 8, 9, 10])])
+def test_shift_invert_pfunit_known_answers(ctx, sigma, idxs):
+    from test_oracle_golden import EXPECTED_10, pencil_10
+    a, b = pencil_10()
+    # embed in N = 16: six decoupled rows with eigenvalue 1e6 (far from every shift)
+    n = 16
+    ap = np.zeros((n, n), dtype=complex)
+    bp = np.zeros((n, n), dtype=complex)
+    ap[:10, :10], bp[:10, :10] = a, b
+    for i in range(10, n):
+        ap[i, i], bp[i, i] = 1.0e6, 1.0
+    for M, label in ((ap, "A"), (bp, "B")):
+        r, c = np.nonzero(M)
+        ctx.import_coo(label, n, r + 1, c + 1, M[r, c])
+    sv = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert", number_of_eigenvalues=4,
+                           maxiter=500, sigma=sigma)
+    cfg = lb.new_arpack_config(n, 2, "I", sv)
+    omega, vr, stats = ctx.shift_invert(cfg, sigma)
+    assert stats["nconv"] == 4
+    omega = omega[np.argsort(omega.real)]
+    assert np.abs(omega - EXPECTED_10[np.array(idxs) - 1]).max() < 1e-12
+
+
+def test_call_order_errors(ctx):
+    c2 = lb.Context()
+    with pytest.raises(lb.LgpuError) as err:
+        c2.factorize(1.0 + 0j)
+    assert err.value.code == -3
+    c2.close()
