@@ -159,6 +159,15 @@ int lgpu_zlarnv(int32_t iseed[4], int32_t n, double* out_ri);
 
 /* Launch / traffic accounting since the last call (for bench.py's gpu_launches claim). */
 int lgpu_counters(lgpu_ctx* ctx, int64_t* kernel_launches, int32_t reset);
+/* Optional per-kernel-class device timing: CUDA events are recorded on the context's stream
+ * around every launch; lgpu_profile_read synchronises and returns the accumulated
+ * milliseconds, launch counts and algorithmic bytes per class, in this order (LGPU_N_KINDS entries):
+ * assemble, factor, matvec, fwd_stage0, fwd_stage, top_stage, bwd_stage, bwd_stage0, dots,
+ * update, scale, gemm, other. */
+#define LGPU_N_KINDS 13
+int lgpu_set_profiling(lgpu_ctx* ctx, int32_t enable);
+int lgpu_profile_read(lgpu_ctx* ctx, double* ms, int64_t* counts, double* algo_bytes,
+                      int32_t nkinds, int32_t reset);
 /* Device time (ms, CUDA events on the context's stream) of the most recent
  * assemble / factorize / arnoldi-loop / extraction phases. */
 int lgpu_phase_times(lgpu_ctx* ctx, double* t_assemble_ms, double* t_factor_ms,

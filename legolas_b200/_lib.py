@@ -81,6 +81,8 @@ SIGNATURES = {
     "lgpu_shift_invert_device": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),
     "lgpu_zlarnv": (C.c_int, [_IP, C.c_int32, _P]),
     "lgpu_counters": (C.c_int, [_P, C.POINTER(C.c_int64), C.c_int32]),
+    "lgpu_set_profiling": (C.c_int, [_P, C.c_int32]),
+    "lgpu_profile_read": (C.c_int, [_P, _DP, C.POINTER(C.c_int64), _DP, C.c_int32, C.c_int32]),
     "lgpu_phase_times": (C.c_int, [_P, _DP, _DP, _DP, _DP]),
 }
 

@@ -238,6 +238,22 @@ class Context:
         self._check(self._lib.lgpu_phase_times(self._h, *[C.byref(x) for x in t]), "phase_times")
         return dict(zip(("assemble_ms", "factor_ms", "iter_ms", "extract_ms"), (x.value for x in t)))
 
+    KINDS = ("assemble", "factor", "matvec", "fwd_stage0", "fwd_stage", "top_stage", "bwd_stage",
+             "bwd_stage0", "dots", "update", "scale", "gemm", "other")
+
+    def set_profiling(self, enable: bool):
+        self._check(self._lib.lgpu_set_profiling(self._h, int(enable)), "set_profiling")
+
+    def profile(self, reset: bool = False) -> dict:
+        """{kernel class: (total ms, launches, algorithmic bytes)}; the times are CUDA-event
+        durations measured on the launching stream around every launch of that class."""
+        n = len(self.KINDS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        nbytes = (C.c_double * n)()
+        self._check(self._lib.lgpu_profile_read(self._h, ms, cnt, nbytes, n, int(reset)), "profile_read")
+        return {k: (ms[i], cnt[i], nbytes[i]) for i, k in enumerate(self.KINDS)}
+
     # ---- assembly
     def assemble(self, settings: Settings, grid: np.ndarray, gauss_grid: np.ndarray,
                  fields: Dict[str, np.ndarray]):

@@ -13,7 +13,7 @@
 #include "../../include/legolas_b200.h"
 #include "arnoldi.cuh"
 #include "assemble.cuh"
-#include "bcr.cuh"
+#include "slu.cuh"
 #include "common.cuh"
 #include "iram.hpp"
 
@@ -84,8 +84,8 @@ struct lgpu_ctx {
   DevBuf<PairItem> d_items;
 
   // factorisation
-  BcrPlan bplan;
-  DevBuf<cd> factors, fwork, rhs, delta, yvec;
+  SluPlan splan;
+  DevBuf<cd> pairs, topfac, fwork, rhs, gvec, xpad;
   DevBuf<int32_t> d_info;
   bool factorized = false;
   cd sigma{0.0, 0.0};
@@ -99,15 +99,15 @@ struct lgpu_ctx {
   PinnedBuf<cd> h_stage;
   PinnedBuf<double> h_scal;
 
-  int64_t launches = 0;
+  LaunchLog log;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double t_assemble = 0, t_factor = 0, t_iter = 0, t_extract = 0;
 
   bool assembled() const { return have[0] && have[1]; }
-  BcrDevice bdev() {
-    BcrDevice d{};
-    d.A = A.p; d.B = B.p; d.factors = factors.p; d.work = fwork.p; d.rhs = rhs.p;
-    d.delta = delta.p; d.yvec = yvec.p; d.info = d_info.p;
+  SluDevice sdev() {
+    SluDevice d{};
+    d.A = A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
+    d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
     return d;
   }
 };
@@ -220,12 +220,13 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
   DevicePlan dn{pn.nslots(), static_cast<int32_t>(pn.items.size()), c->d_plan_i32.p + o_sb_n,
                 c->d_plan_i32.p + o_t_n, c->d_items.p + pe.items.size()};
 
+  c->log.stream = c->stream;
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
   launch_assemble(p, de, fields, d_grid, d_gauss, c->A.p, c->B.p, c->masks.p, c->stream);
   launch_boundaries(p, dn, fields, d_grid, d_gauss, c->A.p, c->B.p, c->masks.p, c->natmasks.p,
                     c->d_plan_i32.p + o_el, static_cast<int>(essl.size()), c->d_plan_i32.p + o_er,
                     static_cast<int>(essr.size()), c->stream);
-  c->launches += 2;
+  c->log.launches += 2;
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
   CUDA_CHECK(cudaEventSynchronize(c->ev1));
   float ms = 0.f;
@@ -237,20 +238,21 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
 
 int do_factorize(lgpu_ctx* c, cd sigma) {
   if (!c->assembled()) return fail(c, LGPU_ESTATE, "factorize: matrices not assembled");
-  if (c->bplan.n != c->G) {
-    c->bplan = make_bcr_plan(c->G, env_int("LGPU_BCR_M0", 5), env_int("LGPU_BCR_M1", 4),
-                             env_int("LGPU_BCR_TOP", 32));
-    c->factors.ensure(c->bplan.factor_blocks * BLK2);
-    c->fwork.ensure(c->bplan.work_blocks * BLK2);
-    c->rhs.ensure(c->bplan.rhs_vecs * BLK);
-    c->delta.ensure(c->bplan.delta_vecs * BLK);
-    c->yvec.ensure(static_cast<size_t>(c->N));
+  if (c->splan.n != c->G) {
+    c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 4),
+                             env_int("LGPU_SLU_TOP", 32));
+    c->pairs.ensure(std::max<size_t>(c->splan.pair_records, 1) * PAIR_STRIDE);
+    c->topfac.ensure(TOP_STRIDE);
+    c->fwork.ensure(c->splan.work_rows * ROW_STRIDE);
+    c->rhs.ensure(c->splan.rhs_vecs * SB);
+    c->gvec.ensure(std::max<size_t>(c->splan.pair_records, 1) * SB);
+    c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
     c->d_info.ensure(1);
-    CUDA_CHECK(cudaMemsetAsync(c->delta.p, 0, c->bplan.delta_vecs * BLK * sizeof(cd), c->stream));
   }
   ensure_vectors(c);
+  c->log.stream = c->stream;
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
-  bcr_factorize(c->bplan, c->bdev(), sigma, c->stream, &c->launches);
+  slu_factorize(c->splan, c->sdev(), sigma, c->stream, &c->log);
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
   int32_t info = 0;
   CUDA_CHECK(cudaMemcpyAsync(&info, c->d_info.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -271,20 +273,20 @@ void dev_solve(lgpu_ctx* c, const cd* b, cd* x, int refine) {
     CUDA_CHECK(cudaMemcpyAsync(c->vr.p, b, sizeof(cd) * c->N, cudaMemcpyDeviceToDevice, c->stream));
     rhs = c->vr.p;
   }
-  bcr_solve(c->bplan, c->bdev(), rhs, x, c->stream, &c->launches);
+  slu_solve(c->splan, c->sdev(), rhs, x, c->stream, &c->log);
   for (int it = 0; it < refine; ++it) {
     // e = M^-1 (b - (A - sigma B) x) ; x += e
     block_matvec(c->G, c->A.p, c->B.p, cd{-1.0, 0.0}, c->sigma, x, rhs, c->ve.p, c->stream,
-                 &c->launches);
-    bcr_solve(c->bplan, c->bdev(), c->ve.p, c->ve.p, c->stream, &c->launches);
-    vec_axpby(c->N, cd{1.0, 0.0}, x, cd{1.0, 0.0}, c->ve.p, c->stream, &c->launches);
+                 &c->log);
+    slu_solve(c->splan, c->sdev(), c->ve.p, c->ve.p, c->stream, &c->log);
+    vec_axpby(c->N, cd{1.0, 0.0}, x, cd{1.0, 0.0}, c->ve.p, c->stream, &c->log);
   }
 }
 
 // y = M^-1 B x on the device (x, y may alias)
 void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
   block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, c->vu.p, c->stream,
-               &c->launches);
+               &c->log);
   dev_solve(c, c->vu.p, y, refine);
 }
 
@@ -299,17 +301,17 @@ class CudaKrylovOps final : public KrylovOps {
     const KrylovWork kw = kwork(c_);
     cd* V = c_->V.p;
     cd* H = c_->Hdev.p;
-    if (k == 0) krylov_norm(n, c_->resid.p, kw, c_->stream, &c_->launches);
+    if (k == 0) krylov_norm(n, c_->resid.p, kw, c_->stream, &c_->log);
     for (int j = k; j < m; ++j) {
       cd* vj = V + static_cast<size_t>(j) * n;
       cd* hsub = j > 0 ? H + static_cast<size_t>(j - 1) * ncv_ + j : nullptr;
-      krylov_scale(n, c_->resid.p, vj, kw, hsub, c_->stream, &c_->launches);
+      krylov_scale(n, c_->resid.p, vj, kw, hsub, c_->stream, &c_->log);
       dev_apply_op(c_, vj, c_->resid.p, refine_);
       cd* hcol = H + static_cast<size_t>(j) * ncv_;
-      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->launches);
-      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->launches);
-      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->launches);
-      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->launches);
+      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->log);
+      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
+      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
+      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
     }
   }
 
@@ -350,10 +352,10 @@ class CudaKrylovOps final : public KrylovOps {
     const int n = c_->N;
     upload_small(Q, ldq, kplusp, kev + 1 <= kplusp ? kev + 1 : kplusp);
     const int nc = kev + 1 <= kplusp ? kev + 1 : kplusp;
-    basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nc, c_->V.p, n, c_->stream, &c_->launches);
+    basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nc, c_->V.p, n, c_->stream, &c_->log);
     vec_axpby(n, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
-              c_->V.p + static_cast<size_t>(kev) * n, c_->stream, &c_->launches);
-    krylov_norm(n, c_->resid.p, kwork(c_), c_->stream, &c_->launches);
+              c_->V.p + static_cast<size_t>(kev) * n, c_->stream, &c_->log);
+    krylov_norm(n, c_->resid.p, kwork(c_), c_->stream, &c_->log);
     // the staging buffer is reused by the next fetch(): make sure the upload has been consumed
     CUDA_CHECK(cudaStreamSynchronize(c_->stream));
   }
@@ -362,7 +364,7 @@ class CudaKrylovOps final : public KrylovOps {
     const int n = c_->N;
     upload_small(S, lds, kplusp, nconv);
     basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nconv, c_->Z.p, n, c_->stream,
-               &c_->launches);
+               &c_->log);
   }
 
  private:
@@ -636,8 +638,7 @@ int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const 
     if (which < 0 || which > 1 || n <= 0 || n % BLK != 0 || nnz < 0)
       return fail(ctx, LGPU_EINVAL, "import_coo: n must be a positive multiple of 16");
     const int G = n / BLK;
-    if (ctx->have[1 - which] && ctx->G != G)
-      return fail(ctx, LGPU_EINVAL, "import_coo: A and B dimensions differ");
+    if (ctx->have[1 - which] && ctx->G != G) ctx->have[1 - which] = false;   // new problem size
     const size_t cnt = static_cast<size_t>(G) * 3 * BLK2;
     std::vector<cd> blocks(cnt, cd{0.0, 0.0});
     std::vector<uint32_t> masks(static_cast<size_t>(G) * MASK_WORDS, 0u);
@@ -662,7 +663,7 @@ int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const 
     ctx->G = G;
     ctx->N = n;
     ctx->factorized = false;
-    ctx->bplan.n = ctx->bplan.n == G ? G : 0;
+    if (ctx->splan.n != G) ctx->splan.n = 0;
     (which ? ctx->B : ctx->A).ensure(cnt);
     ctx->masks.ensure(masks.size());
     ctx->natmasks.ensure(2 * 2 * 4 * 8 + 2);
@@ -704,7 +705,7 @@ int lgpu_matvec(lgpu_ctx* ctx, int32_t which, const double* x_ri, double* y_ri) 
     CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, x_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
     block_matvec(ctx->G, ctx->A.p, ctx->B.p, cd{which == 0 ? 1.0 : 0.0, 0.0},
                  cd{which == 1 ? 1.0 : 0.0, 0.0}, ctx->vx.p, nullptr, ctx->vy.p, ctx->stream,
-                 &ctx->launches);
+                 &ctx->log);
     CUDA_CHECK(cudaMemcpyAsync(y_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LGPU_OK;
@@ -769,9 +770,34 @@ int lgpu_zlarnv(int32_t iseed[4], int32_t n, double* out_ri) {
 
 int lgpu_counters(lgpu_ctx* ctx, int64_t* kernel_launches, int32_t reset) {
   if (!ctx) return LGPU_EINVAL;
-  if (kernel_launches) *kernel_launches = ctx->launches;
-  if (reset) ctx->launches = 0;
+  if (kernel_launches) *kernel_launches = ctx->log.launches;
+  if (reset) ctx->log.launches = 0;
   return LGPU_OK;
+}
+
+int lgpu_set_profiling(lgpu_ctx* ctx, int32_t enable) {
+  return guarded(ctx, [&] {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->log.stream = ctx->stream;
+    ctx->log.reset();
+    ctx->log.profiling = enable != 0;
+    return LGPU_OK;
+  });
+}
+
+int lgpu_profile_read(lgpu_ctx* ctx, double* ms, int64_t* counts, double* algo_bytes,
+                      int32_t nkinds, int32_t reset) {
+  return guarded(ctx, [&] {
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->log.collect();
+    for (int k = 0; k < nkinds && k < LK_COUNT; ++k) {
+      if (ms) ms[k] = ctx->log.ms[k];
+      if (counts) counts[k] = ctx->log.count[k];
+      if (algo_bytes) algo_bytes[k] = ctx->log.bytes[k];
+    }
+    if (reset) ctx->log.reset();
+    return LGPU_OK;
+  });
 }
 
 int lgpu_phase_times(lgpu_ctx* ctx, double* t_assemble_ms, double* t_factor_ms, double* t_iter_ms,

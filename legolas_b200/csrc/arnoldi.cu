@@ -159,39 +159,47 @@ int tiles(int n) { return (n + KRYLOV_TILE - 1) / KRYLOV_TILE; }
 }  // namespace
 
 void krylov_dots(int n, const cd* V, int ldv, int ncols, const cd* w, const KrylovWork& work,
-                 cd* Hcol, int accumulate, cudaStream_t stream, int64_t* launches) {
+                 cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log) {
+  log->begin(LK_DOTS, 16.0 * n * (ncols + 1));
   krylov_dots_kernel<<<tiles(n), 256, 0, stream>>>(n, V, ldv, ncols, w, work.partial, work.hwork,
                                                    Hcol, accumulate, work.ticket);
-  *launches += 1;
+  log->end();
+  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 
 void krylov_update(int n, const cd* V, int ldv, int ncols, cd* w, const KrylovWork& work,
-                   cudaStream_t stream, int64_t* launches) {
+                   cudaStream_t stream, LaunchLog* log) {
+  log->begin(LK_UPDATE, 16.0 * n * (ncols + 2));
   krylov_update_kernel<<<tiles(n), 256, 0, stream>>>(n, V, ldv, ncols, w, work.hwork,
                                                      work.partial, work.scal, work.ticket);
-  *launches += 1;
+  log->end();
+  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 
 void krylov_norm(int n, const cd* w, const KrylovWork& work, cudaStream_t stream,
-                 int64_t* launches) {
+                 LaunchLog* log) {
+  log->begin(LK_UPDATE, 16.0 * n);
   krylov_update_kernel<<<tiles(n), 256, 0, stream>>>(n, nullptr, 0, 0, const_cast<cd*>(w),
                                                      work.hwork, work.partial, work.scal,
                                                      work.ticket);
-  *launches += 1;
+  log->end();
+  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 
 void krylov_scale(int n, const cd* w, cd* vout, const KrylovWork& work, cd* hsub,
-                  cudaStream_t stream, int64_t* launches) {
+                  cudaStream_t stream, LaunchLog* log) {
+  log->begin(LK_SCALE, 32.0 * n);
   krylov_scale_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, w, vout, work.scal, hsub);
-  *launches += 1;
+  log->end();
+  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 
 void basis_gemm(int n, const cd* V, int ldv, int nk, const cd* Q, int ldq, int nc, cd* Out,
-                int ldo, cudaStream_t stream, int64_t* launches) {
+                int ldo, cudaStream_t stream, LaunchLog* log) {
   const size_t smem = sizeof(cd) * (static_cast<size_t>(nk) * nc + static_cast<size_t>(nk) * 32);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -199,14 +207,18 @@ void basis_gemm(int n, const cd* V, int ldv, int nk, const cd* Q, int ldq, int n
                                     static_cast<int>(smem)));
     configured = smem;
   }
+  log->begin(LK_GEMM, 16.0 * n * (nk + nc));
   basis_gemm_kernel<<<(n + 31) / 32, 256, smem, stream>>>(n, V, ldv, nk, Q, ldq, nc, Out, ldo);
-  *launches += 1;
+  log->end();
+  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 
-void vec_axpby(int n, cd a, cd* r, cd b, const cd* v, cudaStream_t stream, int64_t* launches) {
+void vec_axpby(int n, cd a, cd* r, cd b, const cd* v, cudaStream_t stream, LaunchLog* log) {
+  log->begin(LK_OTHER, 48.0 * n);
   vec_axpby_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, a, r, b, v);
-  *launches += 1;
+  log->end();
+  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 

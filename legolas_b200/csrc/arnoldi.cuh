@@ -26,21 +26,21 @@ struct KrylovWork {
 // h = V(:, 0:ncols)^H w  -> work.hwork ; Hcol (device, may be null) gets `=` (accumulate == 0)
 // or `+=` (accumulate == 1).
 void krylov_dots(int n, const cd* V, int ldv, int ncols, const cd* w, const KrylovWork& work,
-                 cd* Hcol, int accumulate, cudaStream_t stream, int64_t* launches);
+                 cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log);
 // w -= V(:, 0:ncols) hwork ; afterwards scal[0] = ||w||_2
 void krylov_update(int n, const cd* V, int ldv, int ncols, cd* w, const KrylovWork& work,
-                   cudaStream_t stream, int64_t* launches);
+                   cudaStream_t stream, LaunchLog* log);
 // scal[0] = ||w||_2
 void krylov_norm(int n, const cd* w, const KrylovWork& work, cudaStream_t stream,
-                 int64_t* launches);
+                 LaunchLog* log);
 // vout = w / scal[0] ; if hsub != null: *hsub = (scal[0], 0)
 void krylov_scale(int n, const cd* w, cd* vout, const KrylovWork& work, cd* hsub,
-                  cudaStream_t stream, int64_t* launches);
+                  cudaStream_t stream, LaunchLog* log);
 // Out(:, 0:nc) = V(:, 0:nk) Q(0:nk, 0:nc); Q is a device matrix with leading dimension ldq.
 // Out may alias V (row-local update).
 void basis_gemm(int n, const cd* V, int ldv, int nk, const cd* Q, int ldq, int nc, cd* Out,
-                int ldo, cudaStream_t stream, int64_t* launches);
+                int ldo, cudaStream_t stream, LaunchLog* log);
 // r = a*r + b*v
-void vec_axpby(int n, cd a, cd* r, cd b, const cd* v, cudaStream_t stream, int64_t* launches);
+void vec_axpby(int n, cd a, cd* r, cd b, const cd* v, cudaStream_t stream, LaunchLog* log);
 
 }  // namespace lgpu

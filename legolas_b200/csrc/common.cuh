@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace lgpu {
 
@@ -76,5 +77,61 @@ inline void cuda_check(cudaError_t err, const char* what, const char* file, int 
   }
 }
 #define CUDA_CHECK(expr) ::lgpu::cuda_check((expr), #expr, __FILE__, __LINE__)
+
+// Kernel-launch accounting and optional per-kernel-class device timing (CUDA events recorded
+// on the launching stream around each launch; read back at a synchronisation point).
+enum LaunchKind {
+  LK_ASSEMBLE = 0, LK_FACTOR, LK_MATVEC, LK_FWD0, LK_FWD, LK_TOP, LK_BWD, LK_BWD0, LK_DOTS,
+  LK_UPDATE, LK_SCALE, LK_GEMM, LK_OTHER, LK_COUNT
+};
+
+struct LaunchLog {
+  int64_t launches = 0;
+  bool profiling = false;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> pool;   // start/stop pairs
+  std::vector<int> kinds;          // kind of each recorded pair
+  size_t used = 0;                 // events used
+  double ms[LK_COUNT] = {};
+  int64_t count[LK_COUNT] = {};
+  double bytes[LK_COUNT] = {};     // algorithmic bytes of the timed launches
+
+  void begin(int kind, double algo_bytes = 0.0) {
+    if (!profiling) return;
+    bytes[kind] += algo_bytes;
+    if (used + 2 > pool.size()) {
+      const size_t grow = pool.size() ? pool.size() : 4096;
+      for (size_t i = 0; i < grow; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { profiling = false; return; }
+        pool.push_back(e);
+      }
+    }
+    kinds.push_back(kind);
+    cudaEventRecord(pool[used], stream);
+  }
+  void end() {
+    if (!profiling || kinds.size() * 2 <= used) return;
+    cudaEventRecord(pool[used + 1], stream);
+    used += 2;
+  }
+  // requires the stream to be idle
+  void collect() {
+    for (size_t i = 0; i + 1 < used; i += 2) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pool[i], pool[i + 1]) == cudaSuccess) {
+        ms[kinds[i / 2]] += t;
+        count[kinds[i / 2]] += 1;
+      }
+    }
+    used = 0;
+    kinds.clear();
+  }
+  void reset() {
+    collect();
+    for (int k = 0; k < LK_COUNT; ++k) { ms[k] = 0.0; count[k] = 0; bytes[k] = 0.0; }
+  }
+  ~LaunchLog() { for (auto e : pool) cudaEventDestroy(e); }
+};
 
 }  // namespace lgpu

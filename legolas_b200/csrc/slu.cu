@@ -1,0 +1,752 @@
+// K2 / K2' / K3a — see slu.cuh for the algorithm and the reference call sites replaced.
+#include "slu.cuh"
+
+#include <algorithm>
+
+namespace lgpu {
+
+// ============================================================================= plan
+SluPlan make_slu_plan(int n, int first_stage_mu, int next_stage_mu, int top_max_rows) {
+  SluPlan p;
+  p.n = n;
+  p.n_pad = n + (n & 1);
+  p.K = p.n_pad / 2;
+  const int m0 = p.K - 1;
+  p.top_size = m0 >= 1 ? 64 : 32;
+  size_t pairs = 0, rows = 0;
+  int m = m0;
+  while (m > 1) {
+    SluLevel lv{};
+    lv.m = m;
+    lv.npairs = m / 2;
+    lv.off_pairs = pairs; pairs += lv.npairs;
+    lv.off_rows = rows; rows += m;
+    p.levels.push_back(lv);
+    m = (m + 1) / 2;
+  }
+  p.off_rows_final = rows;
+  rows += 1;
+  p.pair_records = pairs;
+  p.work_rows = rows;
+  const int nl = static_cast<int>(p.levels.size());
+  int l0 = 0;
+  size_t rhs = 0;
+  bool first = true;
+  while (true) {
+    const int ml = l0 < nl ? p.levels[l0].m : (m0 >= 1 ? 1 : 0);
+    SluStage st{};
+    st.l0 = l0;
+    st.m0 = ml;
+    st.off_fin = rhs;
+    if (ml <= top_max_rows || l0 >= nl) {
+      st.mu = nl - l0;
+      st.nchunks = 1;
+      rhs += ml;
+      p.stages.push_back(st);
+      break;
+    }
+    st.mu = std::min(first ? first_stage_mu : next_stage_mu, nl - l0);
+    const int C = 1 << st.mu;
+    st.nchunks = (ml + C - 1) / C;
+    rhs += ml;
+    p.stages.push_back(st);
+    l0 += st.mu;
+    first = false;
+  }
+  p.rhs_vecs = rhs + 1;
+  return p;
+}
+
+// ============================================================================ device
+namespace {
+
+__device__ __forceinline__ cd ldg_cd(const cd* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return cd{v.x, v.y};
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ int tri_lo_off(int c) { return c * SB - (c * (c - 1)) / 2; }
+__device__ __forceinline__ int tri_up_off(int k) { return (k * (k + 1)) / 2; }
+
+constexpr int MAX_STAGE_LEVELS = 14;
+
+struct LevelRef {
+  int m;
+  size_t off_pairs;
+};
+
+struct StageArgs {
+  int l0, mu, m0, nchunks;
+  int n, n_pad, K, top_size;
+  LevelRef lv[MAX_STAGE_LEVELS];
+  const cd* pairs;
+  const cd* top;
+  const cd* b;       // original right-hand side (n x 16)
+  const cd* fin;     // stage input rows (m0 x 32)
+  cd* fout;          // stage output rows (nchunks x 32)
+  cd* gvec;
+  cd* xv;            // solution, K x 32
+};
+
+// Forward sweep of one merged pair by one warp.
+//   s: the two stacked right-hand sides (64, shared) ; out: reduced right-hand side (32, shared)
+//   g = L11^-1 (P s)_1  is kept for the back substitution ; out = (P s)_2 - L21 g
+__device__ __forceinline__ void pair_forward(const cd* __restrict__ rec, const cd* s, cd* out,
+                                             cd* __restrict__ gout, cd* scratch, int lane) {
+  const uint8_t* perm = reinterpret_cast<const uint8_t*>(rec + PR_PERM);
+  const cd v1 = s[perm[lane]], v2 = s[perm[SB + lane]];
+  scratch[lane] = v1;
+  __syncwarp();
+  cd g{0.0, 0.0};
+  const cd* L = rec + PR_L11I;
+#pragma unroll 8
+  for (int c = 0; c < SB; ++c)
+    if (lane >= c) cfma(g, ldg_cd(L + tri_lo_off(c) + lane - c), scratch[c]);
+  scratch[SB + lane] = g;
+  gout[lane] = g;
+  __syncwarp();
+  cd acc = v2;
+  const cd* M = rec + PR_L21;
+#pragma unroll 8
+  for (int c = 0; c < SB; ++c) cfms(acc, ldg_cd(M + c * SB + lane), scratch[SB + c]);
+  out[lane] = acc;
+  __syncwarp();
+}
+
+// Back substitution of one merged pair by one warp:  z = U^-1 (g - E z_left - F z_right)
+__device__ __forceinline__ void pair_backward(const cd* __restrict__ rec, const cd* __restrict__ g,
+                                              const cd* zl, const cd* zr, cd* zout,
+                                              cd* __restrict__ xg, cd* ustage, int lane) {
+  for (int e = lane; e < TRI; e += 32) cp_async16(ustage + e, rec + PR_U + e);
+  cp_async_commit();
+  cd r = g[lane];
+  const cd* E = rec + PR_E;
+  const cd* F = rec + PR_F;
+#pragma unroll 8
+  for (int c = 0; c < SB; ++c) cfms(r, ldg_cd(E + c * SB + lane), zl[c]);
+#pragma unroll 8
+  for (int c = 0; c < SB; ++c) cfms(r, ldg_cd(F + c * SB + lane), zr[c]);
+  cp_async_wait_all();
+  __syncwarp();
+#pragma unroll 4
+  for (int k = SB - 1; k >= 0; --k) {
+    const int off = tri_up_off(k);
+    cd xk = r * ustage[off + k];   // diagonal holds 1 / U_kk ; only lane k's value is used
+    xk.x = __shfl_sync(0xffffffffu, xk.x, k);
+    xk.y = __shfl_sync(0xffffffffu, xk.y, k);
+    if (lane < k) cfms(r, ustage[off + lane], xk);
+    else if (lane == k) r = xk;
+  }
+  zout[lane] = r;
+  xg[lane] = r;
+  __syncwarp();
+}
+
+// Reduce the `cnt` rows of a chunk (first row r0 of level l0) to one row; returns the buffer
+// holding it.  Rows merge pairwise, an odd last row is carried up unchanged.
+__device__ __forceinline__ cd* chunk_forward(const StageArgs& a, int r0, int cnt, cd* cur, cd* nxt,
+                                             cd* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int lam = 0; lam < a.mu; ++lam) {
+    const int ml = (cnt + (1 << lam) - 1) >> lam;        // rows of the chunk at this level
+    const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
+    for (int i = warp; i < (ml + 1) / 2; i += nwarps) {
+      if (2 * i + 1 < ml) {
+        const size_t gp = pair0 + i;
+        pair_forward(a.pairs + gp * PAIR_STRIDE, cur + 2 * i * SB, nxt + i * SB,
+                     a.gvec + gp * SB, scratch + warp * 2 * SB, lane);
+      } else {
+        nxt[i * SB + lane] = cur[2 * i * SB + lane];
+      }
+    }
+    __syncthreads();
+    cd* t = cur; cur = nxt; nxt = t;
+  }
+  return cur;
+}
+
+__device__ __forceinline__ size_t unknown_index(const StageArgs& a, int j) {
+  // level-l0 unknown j -> super-node index; the last unknown of every level is node K - 1
+  return j < a.m0 ? (static_cast<size_t>(j) << a.l0) : static_cast<size_t>(a.K - 1);
+}
+
+// z slots 0 and cnt hold the known end unknowns; fill in the interior ones.
+__device__ __forceinline__ void chunk_backward(const StageArgs& a, int r0, int cnt, cd* z,
+                                               cd* ustage) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int lam = a.mu - 1; lam >= 0; --lam) {
+    const int s = 1 << lam;
+    const int ml = (cnt + s - 1) >> lam;
+    const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
+    for (int i = warp; i < ml / 2; i += nwarps) {
+      const int ql = 2 * i * s, qm = ql + s, qr = min(ql + 2 * s, cnt);
+      const size_t gp = pair0 + i;
+      pair_backward(a.pairs + gp * PAIR_STRIDE, a.gvec + gp * SB, z + ql * SB, z + qr * SB,
+                    z + qm * SB, a.xv + unknown_index(a, r0 + qm) * SB, ustage + warp * TRI, lane);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) slu_fwd_stage_kernel(StageArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = 1 << a.mu;
+  cd* buf0 = reinterpret_cast<cd*>(smem_raw);
+  cd* buf1 = buf0 + C * SB;
+  cd* scratch = buf1 + C * SB;           // 8 warps x 64
+  const int r0 = blockIdx.x * C;
+  const int cnt = min(C, a.m0 - r0);
+  for (int e = threadIdx.x; e < cnt * SB; e += blockDim.x)
+    buf0[e] = a.fin[static_cast<size_t>(r0) * SB + e];
+  __syncthreads();
+  const cd* res = chunk_forward(a, r0, cnt, buf0, buf1, scratch);
+  if (threadIdx.x < SB) a.fout[static_cast<size_t>(blockIdx.x) * SB + threadIdx.x] = res[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) slu_bwd_stage_kernel(StageArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = 1 << a.mu;
+  cd* z = reinterpret_cast<cd*>(smem_raw);   // (C + 1) x 32
+  cd* ustage = z + (C + 1) * SB;             // 8 warps x TRI
+  const int r0 = blockIdx.x * C;
+  const int cnt = min(C, a.m0 - r0);
+  if (threadIdx.x < SB) z[threadIdx.x] = a.xv[unknown_index(a, r0) * SB + threadIdx.x];
+  else if (threadIdx.x < 2 * SB)
+    z[cnt * SB + threadIdx.x - SB] = a.xv[unknown_index(a, r0 + cnt) * SB + threadIdx.x - SB];
+  __syncthreads();
+  chunk_backward(a, r0, cnt, z, ustage);
+}
+
+// Single CTA: remaining levels forward, dense top system, back substitution.
+__global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = 1 << a.mu;
+  const int tid = threadIdx.x;
+  cd* buf0 = reinterpret_cast<cd*>(smem_raw);
+  cd* buf1 = buf0 + C * SB;
+  cd* z = buf1 + C * SB;                  // (C + 1) x 32
+  cd* tvec = z + (C + 1) * SB;            // 64 permuted rhs + 64 scratch
+  cd* big = tvec + 128;                   // max(8 * TRI, 64 * 64): U of the top system / U stages
+  const int cnt = a.m0;
+  for (int e = tid; e < cnt * SB; e += blockDim.x) buf0[e] = a.fin[e];
+  __syncthreads();
+  const cd* res = buf0;
+  if (cnt > 0) res = chunk_forward(a, 0, cnt, buf0, buf1, big /*8 x 64 scratch*/);
+  // ---- top system: [boundary row of node 0 ; last reduced row ; boundary row of node n_pad-1]
+  const int TS = a.top_size;
+  __syncthreads();
+  cd* t = big + 64 * 64;   // 64 entries behind the staged U
+  if (tid < 64) {
+    cd v{0.0, 0.0};
+    if (tid < 16) v = a.b[tid];
+    else if (TS == 64 && tid < 48) v = res[tid - 16];
+    else if (tid < TS) {
+      const int e = tid - (TS - 16);
+      if (a.n_pad - 1 < a.n) v = a.b[static_cast<size_t>(a.n_pad - 1) * 16 + e];
+    }
+    t[tid] = v;
+  }
+  for (int e = tid; e < 64 * 64; e += blockDim.x) big[e] = a.top[TOP_U + e];
+  __syncthreads();
+  const uint8_t* perm = reinterpret_cast<const uint8_t*>(a.top);
+  cd y{0.0, 0.0};
+  if (tid < TS) {
+    const cd* Linv = a.top + TOP_LINV;
+    for (int c = 0; c < TS; ++c) cfma(y, ldg_cd(Linv + c * 64 + tid), t[perm[c]]);
+  }
+  __shared__ cd xk_s;
+  for (int k = TS - 1; k >= 0; --k) {
+    if (tid == k) { y = y * big[k * 64 + k]; xk_s = y; }
+    __syncthreads();
+    if (tid < k) cfms(y, big[k * 64 + tid], xk_s);
+    __syncthreads();
+  }
+  if (tid < TS) {
+    const int half = tid >> 5, e = tid & 31;       // half 0: z_0, half 1: z_{K-1}
+    z[(half ? cnt : 0) * SB + e] = y;
+    a.xv[(half ? static_cast<size_t>(a.K - 1) : 0) * SB + e] = y;
+  }
+  __syncthreads();
+  if (cnt > 0) chunk_backward(a, 0, cnt, z, big);
+}
+
+// ------------------------------------------------------------------ factorisation kernels
+struct FactorArgs {
+  const cd* A;
+  const cd* B;
+  cd sigma;
+  int n, n_pad, K;
+  const cd* src;       // work rows of this level
+  cd* dst;             // work rows of the next level
+  cd* pairs;           // pair records of this level
+  cd* top;
+  int m;               // rows at this level
+  int npairs;
+  int level;
+  int top_size;
+  int32_t* info;
+};
+
+// entry (i, j) of tile t (0 sub, 1 diag, 2 super) of block row r of A - sigma*B; the padding
+// node (r >= n) is a decoupled identity row
+__device__ __forceinline__ cd m_entry(const FactorArgs& a, int r, int t, int i, int j) {
+  if (r >= a.n) return cd{(t == 1 && i == j) ? 1.0 : 0.0, 0.0};
+  const size_t off = (static_cast<size_t>(r) * 3 + t) * BLK2 + j * BLK + i;
+  return a.A[off] - a.sigma * a.B[off];
+}
+
+// level-0 rows of the bidiagonal form: row k = block rows (2k+1, 2k+2) on z_k (S) and z_k+1 (T)
+__global__ void __launch_bounds__(256) slu_build_rows_kernel(FactorArgs a) {
+  const int k = blockIdx.x;
+  const int r1 = 2 * k + 1, r2 = 2 * k + 2;
+  cd* S = a.dst + static_cast<size_t>(k) * ROW_STRIDE;
+  cd* T = S + SB2;
+  for (int e = threadIdx.x; e < SB2; e += blockDim.x) {
+    const int row = e & 31, col = e >> 5;
+    const int i = row & 15, j = col & 15;
+    const bool top = row < 16, left = col < 16;
+    cd s{0.0, 0.0}, t{0.0, 0.0};
+    if (top) {
+      s = m_entry(a, r1, left ? 0 : 1, i, j);
+      if (left) t = m_entry(a, r1, 2, i, j);
+    } else {
+      if (!left) s = m_entry(a, r2, 0, i, j);
+      t = m_entry(a, r2, left ? 1 : 2, i, j);
+    }
+    S[e] = s;
+    T[e] = t;
+  }
+}
+
+constexpr int WLD = 97;   // padded row length of the 64 x 96 working matrix
+
+// Merge rows (2p, 2p+1) of a level: GE with partial pivoting over the 64 stacked rows of the
+// panel [T_2p ; S_2p+1]; block npairs (if present) carries the odd last row up unchanged.
+__global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* W = reinterpret_cast<cd*>(smem_raw);          // [64][WLD]
+  cd* X = W + 64 * WLD;                             // [32][33] inverse of L11
+  cd* lcol = X + SB * 33;                           // [64]
+  int* prm = reinterpret_cast<int*>(lcol + 64);     // [64]
+  __shared__ int piv_row;
+  __shared__ double rscale[64];
+  const int tid = threadIdx.x;
+  const int p = blockIdx.x;
+  if (p == a.npairs) {   // odd row out
+    const cd* s = a.src + static_cast<size_t>(a.m - 1) * ROW_STRIDE;
+    cd* d = a.dst + static_cast<size_t>(a.npairs) * ROW_STRIDE;
+    for (int e = tid; e < ROW_STRIDE; e += blockDim.x) d[e] = s[e];
+    return;
+  }
+  const cd* Sa = a.src + static_cast<size_t>(2 * p) * ROW_STRIDE;
+  const cd* Ta = Sa + SB2;
+  const cd* Sc = Sa + ROW_STRIDE;
+  const cd* Tc = Sc + SB2;
+  for (int e = tid; e < SB2; e += blockDim.x) {
+    const int i = e & 31, c = e >> 5;
+    W[i * WLD + c] = Ta[e];
+    W[(32 + i) * WLD + c] = Sc[e];
+    W[i * WLD + 32 + c] = Sa[e];
+    W[(32 + i) * WLD + 32 + c] = cd{0.0, 0.0};
+    W[i * WLD + 64 + c] = cd{0.0, 0.0};
+    W[(32 + i) * WLD + 64 + c] = Tc[e];
+  }
+  if (tid < 64) prm[tid] = tid;
+  __syncthreads();
+  // Row equilibration by exact powers of two.  The finite-element rows of different variables
+  // scale like dx, 1 and 1/dx; partial pivoting on unscaled rows loses 4-5 digits at 10^4 grid
+  // points.  The scales are folded back into the stored factors below.
+  if (tid < 64) {
+    double mx = 0.0;
+    for (int c = 0; c < 96; ++c) mx = fmax(mx, fmax(fabs(W[tid * WLD + c].x), fabs(W[tid * WLD + c].y)));
+    rscale[tid] = (mx > 0.0 && isfinite(mx)) ? exp2(-static_cast<double>(ilogb(mx))) : 1.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < 64 * 96; e += blockDim.x) {
+    const int i = e / 96, c = e - i * 96;
+    W[i * WLD + c] = W[i * WLD + c] * rscale[i];
+  }
+  __syncthreads();
+  for (int k = 0; k < SB; ++k) {
+    if (tid < 32) {
+      // partial pivoting over rows k .. 63 of column k (two candidates per lane)
+      const int i0 = tid, i1 = tid + 32;
+      double b0 = i0 >= k ? abs2(W[i0 * WLD + k]) : -1.0;
+      const double b1 = abs2(W[i1 * WLD + k]);
+      int bi = i0;
+      if (b1 > b0) { b0 = b1; bi = i1; }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, b0, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ob > b0 || (ob == b0 && oi < bi)) { b0 = ob; bi = oi; }
+      }
+      if (tid == 0) {
+        piv_row = bi;
+        if (!(b0 > 0.0)) {   // exactly singular panel column: report like zgbtrf info > 0
+          const long long node = (static_cast<long long>(2 * p + 1) << a.level);
+          atomicCAS(a.info, 0, static_cast<int>(min(2 * node + 1, static_cast<long long>(a.n))));
+          W[bi * WLD + k] = cd{2.2250738585072014e-308, 0.0};
+        }
+      }
+    }
+    __syncthreads();
+    const int pr = piv_row;
+    if (pr != k) {
+      if (tid < 96) {
+        const cd t0 = W[k * WLD + tid];
+        W[k * WLD + tid] = W[pr * WLD + tid];
+        W[pr * WLD + tid] = t0;
+      } else if (tid == 96) {
+        const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0;
+      }
+    }
+    __syncthreads();
+    if (tid > k && tid < 64) {
+      const cd l = W[tid * WLD + k] * crecip(W[k * WLD + k]);
+      lcol[tid] = l;
+      W[tid * WLD + k] = l;   // multiplier kept in place
+    }
+    __syncthreads();
+    for (int e = tid; e < 64 * 96; e += blockDim.x) {
+      const int i = e / 96, c = e - i * 96;
+      if (i > k && c > k) cfms(W[i * WLD + c], lcol[i], W[k * WLD + c]);
+    }
+    __syncthreads();
+  }
+  // X = L11^-1 (unit lower triangular), one column per thread
+  if (tid < SB) {
+    const int c = tid;
+    for (int i = 0; i < SB; ++i) {
+      cd v{i == c ? 1.0 : 0.0, 0.0};
+      if (i > c) {
+        v = cd{0.0, 0.0};
+        for (int j = c; j < i; ++j) cfms(v, W[i * WLD + j], X[j * 33 + c]);
+      }
+      X[i * 33 + c] = (i >= c) ? v : cd{0.0, 0.0};
+    }
+  }
+  __syncthreads();
+  cd* rec = a.pairs + static_cast<size_t>(p) * PAIR_STRIDE;
+  if (tid < 64) reinterpret_cast<uint8_t*>(rec + PR_PERM)[tid] = static_cast<uint8_t>(prm[tid]);
+  for (int e = tid; e < SB2; e += blockDim.x) {
+    const int i = e & 31, c = e >> 5;
+    // scale of pivot row c folded into column c of L11^-1; reduced rows return to their own scale
+    if (i >= c) rec[PR_L11I + tri_lo_off(c) + i - c] = X[i * 33 + c] * rscale[prm[c]];
+    rec[PR_L21 + e] = W[(32 + i) * WLD + c] * (1.0 / rscale[prm[32 + i]]);
+    rec[PR_E + e] = W[i * WLD + 32 + c];
+    rec[PR_F + e] = W[i * WLD + 64 + c];
+    if (i <= c) rec[PR_U + tri_up_off(c) + i] = (i == c) ? crecip(W[i * WLD + c]) : W[i * WLD + c];
+  }
+  cd* Sn = a.dst + static_cast<size_t>(p) * ROW_STRIDE;
+  cd* Tn = Sn + SB2;
+  for (int e = tid; e < SB2; e += blockDim.x) {
+    const int i = e & 31, c = e >> 5;
+    const double unscale = 1.0 / rscale[prm[32 + i]];
+    Sn[e] = W[(32 + i) * WLD + 32 + c] * unscale;
+    Tn[e] = W[(32 + i) * WLD + 64 + c] * unscale;
+  }
+}
+
+constexpr int TLD = 65;
+
+// Dense top system: rows [node 0 ; last reduced row ; node n_pad - 1] on (z_0, z_K-1).
+__global__ void __launch_bounds__(256) slu_top_factor_kernel(FactorArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* W = reinterpret_cast<cd*>(smem_raw);       // [64][TLD]
+  cd* X = W + 64 * TLD;                          // [64][TLD] inverse of L
+  cd* lcol = X + 64 * TLD;
+  int* prm = reinterpret_cast<int*>(lcol + 64);
+  __shared__ int piv_row;
+  __shared__ double rscale[64];
+  const int tid = threadIdx.x;
+  const int TS = a.top_size;
+  const int last = a.n_pad - 1;
+  for (int e = tid; e < 64 * 64; e += blockDim.x) {
+    const int row = e >> 6, col = e & 63;
+    cd v{0.0, 0.0};
+    if (row < TS && col < TS) {
+      if (row < 16) {                                    // block row 0 on z_0 = (x_0, x_1)
+        if (col < 32) v = m_entry(a, 0, col < 16 ? 1 : 2, row, col & 15);
+      } else if (TS == 64 && row < 48) {                 // last reduced row: S on z_0, T on z_K-1
+        const cd* S = a.src;
+        v = col < 32 ? S[col * SB + row - 16] : S[SB2 + (col - 32) * SB + row - 16];
+      } else {                                           // block row n_pad-1 on z_K-1
+        const int i = row - (TS - 16), c0 = col - (TS - 32);
+        if (c0 >= 0) v = m_entry(a, last, c0 < 16 ? 0 : 1, i, c0 & 15);
+      }
+    } else if (row == col) {
+      v = cd{1.0, 0.0};
+    }
+    W[row * TLD + col] = v;
+  }
+  if (tid < 64) prm[tid] = tid;
+  __syncthreads();
+  if (tid < 64) {   // row equilibration, as in the merge kernel
+    double mx = 0.0;
+    for (int c = 0; c < 64; ++c) mx = fmax(mx, fmax(fabs(W[tid * TLD + c].x), fabs(W[tid * TLD + c].y)));
+    rscale[tid] = (mx > 0.0 && isfinite(mx)) ? exp2(-static_cast<double>(ilogb(mx))) : 1.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < 64 * 64; e += blockDim.x) W[(e >> 6) * TLD + (e & 63)] = W[(e >> 6) * TLD + (e & 63)] * rscale[e >> 6];
+  __syncthreads();
+  for (int k = 0; k < TS; ++k) {
+    if (tid < 32) {
+      const int i0 = tid, i1 = tid + 32;
+      double b0 = (i0 >= k && i0 < TS) ? abs2(W[i0 * TLD + k]) : -1.0;
+      const double b1 = (i1 >= k && i1 < TS) ? abs2(W[i1 * TLD + k]) : -1.0;
+      int bi = i0;
+      if (b1 > b0) { b0 = b1; bi = i1; }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, b0, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (ob > b0 || (ob == b0 && oi < bi)) { b0 = ob; bi = oi; }
+      }
+      if (tid == 0) {
+        if (!(b0 > 0.0)) {
+          bi = k;
+          atomicCAS(a.info, 0, a.n);
+          W[k * TLD + k] = cd{2.2250738585072014e-308, 0.0};
+        }
+        piv_row = bi;
+      }
+    }
+    __syncthreads();
+    const int pr = piv_row;
+    if (pr != k) {
+      if (tid < 64) {
+        const cd t0 = W[k * TLD + tid];
+        W[k * TLD + tid] = W[pr * TLD + tid];
+        W[pr * TLD + tid] = t0;
+      } else if (tid == 64) {
+        const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0;
+      }
+    }
+    __syncthreads();
+    if (tid > k && tid < TS) {
+      const cd l = W[tid * TLD + k] * crecip(W[k * TLD + k]);
+      lcol[tid] = l;
+      W[tid * TLD + k] = l;
+    }
+    __syncthreads();
+    for (int e = tid; e < 64 * 64; e += blockDim.x) {
+      const int i = e >> 6, c = e & 63;
+      if (i > k && i < TS && c > k && c < TS) cfms(W[i * TLD + c], lcol[i], W[k * TLD + c]);
+    }
+    __syncthreads();
+  }
+  if (tid < 64) {
+    const int c = tid;
+    for (int i = 0; i < 64; ++i) {
+      cd v{i == c ? 1.0 : 0.0, 0.0};
+      if (i > c && i < TS && c < TS) {
+        v = cd{0.0, 0.0};
+        for (int j = c; j < i; ++j) cfms(v, W[i * TLD + j], X[j * TLD + c]);
+      }
+      X[i * TLD + c] = (i >= c) ? v : cd{0.0, 0.0};
+    }
+  }
+  __syncthreads();
+  if (tid < 64) reinterpret_cast<uint8_t*>(a.top)[tid] = static_cast<uint8_t>(prm[tid]);
+  for (int e = tid; e < 64 * 64; e += blockDim.x) {
+    const int i = e & 63, c = e >> 6;   // column-major, leading dimension 64
+    a.top[TOP_LINV + e] = X[i * TLD + c] * rscale[prm[c]];
+    cd u{0.0, 0.0};
+    if (i < c) u = W[i * TLD + c];
+    else if (i == c) u = crecip(W[i * TLD + c]);
+    a.top[TOP_U + e] = u;
+  }
+}
+
+// ------------------------------------------------------------------------- block matvec
+// y_b = aa * (A x)_b + ab * (B x)_b + z_b ; one warp per block row, 8 rows per CTA.
+template <bool USE_A, bool USE_B>
+__global__ void __launch_bounds__(256)
+block_matvec_kernel(int n, const cd* __restrict__ A, const cd* __restrict__ B, cd aa, cd ab,
+                    const cd* __restrict__ x, const cd* __restrict__ z, cd* __restrict__ y) {
+  __shared__ cd xs[8][3 * BLK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= n) return;
+  cd* xw = xs[warp];
+  for (int e = lane; e < 3 * BLK; e += 32) {
+    const int bb = b - 1 + (e >> 4);
+    xw[e] = (bb >= 0 && bb < n) ? x[static_cast<size_t>(bb) * BLK + (e & 15)] : cd{0.0, 0.0};
+  }
+  __syncwarp();
+  const int i = lane & 15, h = lane >> 4;
+  cd acc_a{0.0, 0.0}, acc_b{0.0, 0.0};
+  const size_t rowoff = static_cast<size_t>(b) * 3 * BLK2;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (USE_A) {
+      cd m[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) m[c] = ldg_cd(A + rowoff + t * BLK2 + (h * 8 + c) * BLK + i);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cfma(acc_a, m[c], xw[t * BLK + h * 8 + c]);
+    }
+    if (USE_B) {
+      cd m[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) m[c] = ldg_cd(B + rowoff + t * BLK2 + (h * 8 + c) * BLK + i);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) cfma(acc_b, m[c], xw[t * BLK + h * 8 + c]);
+    }
+  }
+  cd acc{0.0, 0.0};
+  if (USE_A) acc += aa * acc_a;
+  if (USE_B) acc += ab * acc_b;
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+  acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+  if (lane < BLK) {
+    if (z) acc += z[static_cast<size_t>(b) * BLK + lane];
+    y[static_cast<size_t>(b) * BLK + lane] = acc;
+  }
+}
+
+StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const cd* b, cd* xv) {
+  const SluStage& st = plan.stages[s];
+  StageArgs a{};
+  a.l0 = st.l0; a.mu = st.mu; a.m0 = st.m0; a.nchunks = st.nchunks;
+  a.n = plan.n; a.n_pad = plan.n_pad; a.K = plan.K; a.top_size = plan.top_size;
+  for (int lam = 0; lam < st.mu; ++lam) {
+    const SluLevel& lv = plan.levels[st.l0 + lam];
+    a.lv[lam] = LevelRef{lv.m, lv.off_pairs};
+  }
+  a.pairs = d.pairs;
+  a.top = d.top;
+  a.b = b;
+  a.fin = s == 0 ? b + BLK : d.rhs + st.off_fin * SB;   // level-0 row k = b[(2k+1)*16 ...]
+  const bool top = s == static_cast<int>(plan.stages.size()) - 1;
+  a.fout = top ? nullptr : d.rhs + plan.stages[s + 1].off_fin * SB;
+  a.gvec = d.gvec;
+  a.xv = xv;
+  return a;
+}
+
+size_t fwd_smem(int mu) { return sizeof(cd) * ((2 << mu) * SB + 8 * 2 * SB); }
+size_t bwd_smem(int mu) { return sizeof(cd) * (((1 << mu) + 1) * SB + 8 * TRI); }
+size_t top_smem(int mu) {
+  return sizeof(cd) * ((2 << mu) * SB + ((1 << mu) + 1) * SB + 128 + 64 * 64 + 64 + 8 * TRI);
+}
+constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + SB * 33 + 64) + sizeof(int) * 64;
+constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
+
+void configure_kernels() {
+  static bool done = false;
+  if (done) return;
+  const int big = 200 * 1024;
+  CUDA_CHECK(cudaFuncSetAttribute(slu_fwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_bwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_top_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_top_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  done = true;
+}
+
+}  // namespace
+
+void slu_factorize(const SluPlan& plan, const SluDevice& d, cd sigma, cudaStream_t stream,
+                   LaunchLog* log) {
+  configure_kernels();
+  CUDA_CHECK(cudaMemsetAsync(d.info, 0, sizeof(int32_t), stream));
+  const int nl = static_cast<int>(plan.levels.size());
+  const int m0 = plan.K - 1;
+  log->begin(LK_FACTOR);
+  FactorArgs a{};
+  a.A = d.A; a.B = d.B; a.sigma = sigma; a.n = plan.n; a.n_pad = plan.n_pad; a.K = plan.K;
+  a.top = d.top; a.top_size = plan.top_size; a.info = d.info;
+  auto rows_of = [&](int l) {
+    return d.work + (l < nl ? plan.levels[l].off_rows : plan.off_rows_final) * ROW_STRIDE;
+  };
+  if (m0 >= 1) {
+    a.dst = rows_of(0);
+    slu_build_rows_kernel<<<m0, 256, 0, stream>>>(a);
+    log->launches += 1;
+  }
+  for (int l = 0; l < nl; ++l) {
+    const SluLevel& lv = plan.levels[l];
+    a.src = rows_of(l);
+    a.dst = rows_of(l + 1);
+    a.pairs = d.pairs + lv.off_pairs * PAIR_STRIDE;
+    a.m = lv.m;
+    a.npairs = lv.npairs;
+    a.level = l;
+    slu_merge_kernel<<<lv.npairs + (lv.m & 1), 256, MERGE_SMEM, stream>>>(a);
+    log->launches += 1;
+  }
+  a.src = rows_of(nl);
+  slu_top_factor_kernel<<<1, 256, TOPF_SMEM, stream>>>(a);
+  log->end();
+  log->launches += 1;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Algorithmic bytes of one stage launch: the share of LAPACK's band-LU factor an equivalent
+// zgbtrs sweep streams for the grid points this stage eliminates (forward: 31 multipliers per
+// column = 7936 B per grid point, backward: 63 entries of U per column = 16128 B), plus the
+// right-hand-side / solution vectors it must touch.
+static double stage_algo_bytes(const SluPlan& plan, int s, double per_point) {
+  const SluStage& st = plan.stages[s];
+  double pairs = 0.0;
+  for (int lam = 0; lam < st.mu; ++lam) pairs += plan.levels[st.l0 + lam].npairs;
+  return pairs * 2.0 * per_point + 512.0 * (st.m0 + st.nchunks);
+}
+
+void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
+               LaunchLog* log) {
+  configure_kernels();
+  const int ns = static_cast<int>(plan.stages.size());
+  cd* xv = plan.n_pad == plan.n ? x : d.xpad;
+  for (int s = 0; s < ns - 1; ++s) {
+    const StageArgs a = make_stage_args(plan, d, s, b, xv);
+    log->begin(s == 0 ? LK_FWD0 : LK_FWD, stage_algo_bytes(plan, s, 7936.0));
+    slu_fwd_stage_kernel<<<a.nchunks, 256, fwd_smem(a.mu), stream>>>(a);
+    log->end();
+  }
+  {
+    const StageArgs a = make_stage_args(plan, d, ns - 1, b, xv);
+    log->begin(LK_TOP, stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2);
+    slu_top_stage_kernel<<<1, 256, top_smem(a.mu), stream>>>(a);
+    log->end();
+  }
+  for (int s = ns - 2; s >= 0; --s) {
+    const StageArgs a = make_stage_args(plan, d, s, b, xv);
+    log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
+    slu_bwd_stage_kernel<<<a.nchunks, 256, bwd_smem(a.mu), stream>>>(a);
+    log->end();
+  }
+  log->launches += 2 * (ns - 1) + 1;
+  if (xv != x) {
+    CUDA_CHECK(cudaMemcpyAsync(x, xv, sizeof(cd) * plan.n * BLK, cudaMemcpyDeviceToDevice, stream));
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+static inline int use_a_count(cd v) { return (v.x != 0.0 || v.y != 0.0) ? 1 : 0; }
+
+void block_matvec(int n, const cd* A, const cd* B, cd aa, cd ab, const cd* x, const cd* z, cd* y,
+                  cudaStream_t stream, LaunchLog* log) {
+  const int ctas = (n + 7) / 8;
+  log->begin(LK_MATVEC, ((use_a_count(aa) + use_a_count(ab)) * 12288.0 + (z ? 768.0 : 512.0)) * n);
+  const bool use_a = aa.x != 0.0 || aa.y != 0.0, use_b = ab.x != 0.0 || ab.y != 0.0;
+  if (use_a && use_b) block_matvec_kernel<true, true><<<ctas, 256, 0, stream>>>(n, A, B, aa, ab, x, z, y);
+  else if (use_a) block_matvec_kernel<true, false><<<ctas, 256, 0, stream>>>(n, A, B, aa, ab, x, z, y);
+  else block_matvec_kernel<false, true><<<ctas, 256, 0, stream>>>(n, A, B, aa, ab, x, z, y);
+  log->end();
+  log->launches += 1;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace lgpu

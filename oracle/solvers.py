@@ -133,3 +133,44 @@ def qr_invert(A_dense, B_dense):
     """Dense B^-1 A then zgeev (smod_qr_invert.f08:46-135); small grids only."""
     C = scipy.linalg.solve(B_dense, A_dense)
     return scipy.linalg.eigvals(C)
+
+
+def _blocktri_matvec_ld(blocks_ld, x_ld):
+    d = blocks_ld.shape[-1]
+    xb = x_ld.reshape(-1, d)
+    y = np.einsum("bij,bj->bi", blocks_ld[:, 1], xb)
+    y[1:] += np.einsum("bij,bj->bi", blocks_ld[1:, 0], xb[:-1])
+    y[:-1] += np.einsum("bij,bj->bi", blocks_ld[:-1, 2], xb[1:])
+    return y.reshape(-1)
+
+
+def shift_invert_extended(A, B, sigma, nev, ncv=0, maxiter=0, tol=0.0, which="LM", v0=None,
+                          sweeps=4):
+    """Arbiter for ill-conditioned eigenvalues: the same ARPACK run, but every OP*x is made
+    forward-accurate by iterative refinement with residuals in 80-bit extended precision
+    (A, B: oracle.assembly.BlockTriMatrix).  Slow (small grids only).  Used by the parity
+    tests when the LAPACK-based path and the GPU path disagree beyond 1e-8: both are backward
+    stable, so the one closer to this result is the better answer."""
+    n = A.n
+    ncv, maxiter, tol = arpack_defaults(n, nev, ncv, maxiter, tol)
+    if v0 is None:
+        v0 = zlarnv(n)
+    kl = ku = 2 * A.d - 1
+    lu = BandedLU(A.to_band() - sigma * B.to_band(), kl, ku)
+    M_ld = (A.blocks - sigma * B.blocks).astype(np.clongdouble)
+    B_ld = B.blocks.astype(np.clongdouble)
+
+    def op(x):
+        b = _blocktri_matvec_ld(B_ld, x.astype(np.clongdouble))
+        y = lu.solve(b.astype(np.complex128)).astype(np.clongdouble)
+        for _ in range(sweeps):
+            r = b - _blocktri_matvec_ld(M_ld, y)
+            y = y + lu.solve(r.astype(np.complex128)).astype(np.clongdouble)
+        return y.astype(np.complex128)
+
+    OP = LinearOperator((n, n), matvec=op, dtype=np.complex128)
+    try:
+        nu, vr = eigs(OP, k=nev, which=which, ncv=ncv, maxiter=maxiter, tol=tol, v0=v0.copy())
+    except ArpackNoConvergence as exc:
+        nu, vr = exc.eigenvalues, exc.eigenvectors
+    return sigma + 1.0 / nu, vr
