@@ -97,77 +97,182 @@ struct StageArgs {
   cd* xv;            // solution, K x 32
 };
 
-// Forward sweep of one merged pair by one warp.
-//   s: the two stacked right-hand sides (64, shared) ; out: reduced right-hand side (32, shared)
-//   g = L11^-1 (P s)_1  is kept for the back substitution ; out = (P s)_2 - L21 g
-__device__ __forceinline__ void pair_forward(const cd* __restrict__ rec, const cd* s, cd* out,
-                                             cd* __restrict__ gout, cd* scratch, int lane) {
-  const uint8_t* perm = reinterpret_cast<const uint8_t*>(rec + PR_PERM);
-  const cd v1 = s[perm[lane]], v2 = s[perm[SB + lane]];
-  scratch[lane] = v1;
-  __syncwarp();
-  cd g{0.0, 0.0};
-  const cd* L = rec + PR_L11I;
-#pragma unroll 8
-  for (int c = 0; c < SB; ++c)
-    if (lane >= c) cfma(g, ldg_cd(L + tri_lo_off(c) + lane - c), scratch[c]);
-  scratch[SB + lane] = g;
-  gout[lane] = g;
-  __syncwarp();
-  cd acc = v2;
-  const cd* M = rec + PR_L21;
-#pragma unroll 8
-  for (int c = 0; c < SB; ++c) cfms(acc, ldg_cd(M + c * SB + lane), scratch[SB + c]);
-  out[lane] = acc;
-  __syncwarp();
+// ---- cooperative pair operations ----------------------------------------------------------
+// A pair is processed by a group of GW warps (GW = 1, 2, 4, 8): at the wide lower levels every
+// warp owns a pair, at the narrow upper levels all 8 warps share one so that each lane has
+// only 64 / GW independent 16-byte loads to wait for.  The 32 x 32 matvecs are split by
+// columns across the warps of a group; partial sums meet in shared memory.
+struct Group {
+  int wg;     // warp index inside the group
+  int gid;    // group index inside the CTA (named barrier gid + 1)
+};
+
+template <int GW>
+__device__ __forceinline__ void group_sync(const Group& g) {
+  if (GW == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g.gid + 1), "r"(GW * 32) : "memory");
 }
 
-// Back substitution of one merged pair by one warp:  z = U^-1 (g - E z_left - F z_right)
+__device__ __forceinline__ cd shfl_cd(cd v, int src) {
+  return cd{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
+}
+
+// Forward sweep of one merged pair.
+//   s: the two stacked right-hand sides (64, shared) ; out: reduced right-hand side (32, shared)
+//   g = L11^-1 (P s)_1  is kept for the back substitution ; out = (P s)_2 - L21 g
+//   part: GW x 32 partial sums (shared, private to the group)
+template <int GW>
+__device__ __forceinline__ void pair_forward(const cd* __restrict__ rec, const cd* s, cd* out,
+                                             cd* __restrict__ gout, cd* part, const Group& grp,
+                                             int lane) {
+  constexpr int CW = SB / GW;   // columns per warp
+  const uint8_t* perm = reinterpret_cast<const uint8_t*>(rec + PR_PERM);
+  const cd v1 = s[perm[lane]], v2 = s[perm[SB + lane]];
+  const int c0 = grp.wg * CW;
+  const cd* L = rec + PR_L11I;
+  cd g{0.0, 0.0};
+  {
+    cd m[CW > 16 ? 16 : CW];
+#pragma unroll
+    for (int cb = 0; cb < CW; cb += 16) {
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) {
+        const int col = c0 + cb + c;
+        m[c] = lane >= col ? ldg_cd(L + tri_lo_off(col) + lane - col) : cd{0.0, 0.0};
+      }
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(g, m[c], shfl_cd(v1, c0 + cb + c));
+    }
+  }
+  if (GW > 1) {
+    part[grp.wg * SB + lane] = g;
+    group_sync<GW>(grp);
+    g = cd{0.0, 0.0};
+#pragma unroll
+    for (int w = 0; w < GW; ++w) g += part[w * SB + lane];
+    group_sync<GW>(grp);
+  }
+  const cd* M = rec + PR_L21;
+  cd acc{0.0, 0.0};
+  {
+    cd m[CW > 16 ? 16 : CW];
+#pragma unroll
+    for (int cb = 0; cb < CW; cb += 16) {
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) m[c] = ldg_cd(M + (c0 + cb + c) * SB + lane);
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(acc, m[c], shfl_cd(g, c0 + cb + c));
+    }
+  }
+  if (GW > 1) {
+    part[grp.wg * SB + lane] = acc;
+    group_sync<GW>(grp);
+    if (grp.wg == 0) {
+      acc = cd{0.0, 0.0};
+#pragma unroll
+      for (int w = 0; w < GW; ++w) acc += part[w * SB + lane];
+    }
+  }
+  if (grp.wg == 0) {
+    out[lane] = v2 - acc;
+    gout[lane] = g;
+  }
+  group_sync<GW>(grp);
+}
+
+// Back substitution of one merged pair:  z = U^-1 (g - E z_left - F z_right)
+template <int GW>
 __device__ __forceinline__ void pair_backward(const cd* __restrict__ rec, const cd* __restrict__ g,
                                               const cd* zl, const cd* zr, cd* zout,
-                                              cd* __restrict__ xg, cd* ustage, int lane) {
-  for (int e = lane; e < TRI; e += 32) cp_async16(ustage + e, rec + PR_U + e);
+                                              cd* __restrict__ xg, cd* ustage, cd* part,
+                                              const Group& grp, int lane) {
+  constexpr int CW = SB / GW;
+  for (int e = grp.wg * 32 + lane; e < TRI; e += GW * 32) cp_async16(ustage + e, rec + PR_U + e);
   cp_async_commit();
-  cd r = g[lane];
+  const int c0 = grp.wg * CW;
   const cd* E = rec + PR_E;
   const cd* F = rec + PR_F;
-#pragma unroll 8
-  for (int c = 0; c < SB; ++c) cfms(r, ldg_cd(E + c * SB + lane), zl[c]);
-#pragma unroll 8
-  for (int c = 0; c < SB; ++c) cfms(r, ldg_cd(F + c * SB + lane), zr[c]);
-  cp_async_wait_all();
-  __syncwarp();
-#pragma unroll 4
-  for (int k = SB - 1; k >= 0; --k) {
-    const int off = tri_up_off(k);
-    cd xk = r * ustage[off + k];   // diagonal holds 1 / U_kk ; only lane k's value is used
-    xk.x = __shfl_sync(0xffffffffu, xk.x, k);
-    xk.y = __shfl_sync(0xffffffffu, xk.y, k);
-    if (lane < k) cfms(r, ustage[off + lane], xk);
-    else if (lane == k) r = xk;
+  cd acc{0.0, 0.0};
+  {
+    cd m[CW > 16 ? 16 : CW];
+#pragma unroll
+    for (int cb = 0; cb < CW; cb += 16) {
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) m[c] = ldg_cd(E + (c0 + cb + c) * SB + lane);
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(acc, m[c], zl[c0 + cb + c]);
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) m[c] = ldg_cd(F + (c0 + cb + c) * SB + lane);
+#pragma unroll
+      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(acc, m[c], zr[c0 + cb + c]);
+    }
   }
-  zout[lane] = r;
-  xg[lane] = r;
-  __syncwarp();
+  if (GW > 1) part[grp.wg * SB + lane] = acc;
+  cp_async_wait_all();
+  group_sync<GW>(grp);
+  if (grp.wg == 0) {
+    if (GW > 1) {
+      acc = cd{0.0, 0.0};
+#pragma unroll
+      for (int w = 0; w < GW; ++w) acc += part[w * SB + lane];
+    }
+    cd r = g[lane] - acc;
+#pragma unroll 4
+    for (int k = SB - 1; k >= 0; --k) {
+      const int off = tri_up_off(k);
+      const cd xk = shfl_cd(r * ustage[off + k], k);   // diagonal holds 1 / U_kk
+      if (lane < k) cfms(r, ustage[off + lane], xk);
+      else if (lane == k) r = xk;
+    }
+    zout[lane] = r;
+    xg[lane] = r;
+  }
+  group_sync<GW>(grp);
+}
+
+// warps per pair for a level with np pairs in the chunk (8 warps per CTA)
+__device__ __forceinline__ int group_width(int np) { return np >= 5 ? 1 : (np >= 3 ? 2 : (np == 2 ? 4 : 8)); }
+
+// Pull the factor records a chunk will need at its upper levels into L2 while the first
+// level streams from HBM (the records do not depend on the right-hand side).
+__device__ __forceinline__ void prefetch_records(const StageArgs& a, int r0, int cnt, int lam0,
+                                                 int first, int last) {
+  for (int lam = lam0; lam < a.mu; ++lam) {
+    const int ml = (cnt + (1 << lam) - 1) >> lam;
+    const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
+    const int lines = (last - first) / 8;   // 128-byte lines per record part
+    for (int e = threadIdx.x; e < (ml / 2) * lines; e += blockDim.x) {
+      const cd* p = a.pairs + (pair0 + e / lines) * PAIR_STRIDE + first + (e % lines) * 8;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
 }
 
 // Reduce the `cnt` rows of a chunk (first row r0 of level l0) to one row; returns the buffer
 // holding it.  Rows merge pairwise, an odd last row is carried up unchanged.
 __device__ __forceinline__ cd* chunk_forward(const StageArgs& a, int r0, int cnt, cd* cur, cd* nxt,
                                              cd* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int lam = 0; lam < a.mu; ++lam) {
     const int ml = (cnt + (1 << lam) - 1) >> lam;        // rows of the chunk at this level
+    const int np = ml / 2;
     const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-    for (int i = warp; i < (ml + 1) / 2; i += nwarps) {
-      if (2 * i + 1 < ml) {
-        const size_t gp = pair0 + i;
-        pair_forward(a.pairs + gp * PAIR_STRIDE, cur + 2 * i * SB, nxt + i * SB,
-                     a.gvec + gp * SB, scratch + warp * 2 * SB, lane);
-      } else {
-        nxt[i * SB + lane] = cur[2 * i * SB + lane];
-      }
+    const int gw = group_width(np);
+    const Group grp{warp % gw, warp / gw};
+    const int ngroups = 8 / gw;
+    cd* part = scratch + grp.gid * gw * 2 * SB;
+    for (int i = grp.gid; i < np; i += ngroups) {
+      const size_t gp = pair0 + i;
+      const cd* rec = a.pairs + gp * PAIR_STRIDE;
+      const cd* s = cur + 2 * i * SB;
+      cd* out = nxt + i * SB;
+      cd* gout = a.gvec + gp * SB;
+      if (gw == 1) pair_forward<1>(rec, s, out, gout, part, grp, lane);
+      else if (gw == 2) pair_forward<2>(rec, s, out, gout, part, grp, lane);
+      else if (gw == 4) pair_forward<4>(rec, s, out, gout, part, grp, lane);
+      else pair_forward<8>(rec, s, out, gout, part, grp, lane);
     }
+    if ((ml & 1) && warp == 7) nxt[np * SB + lane] = cur[2 * np * SB + lane];
     __syncthreads();
     cd* t = cur; cur = nxt; nxt = t;
   }
@@ -180,18 +285,30 @@ __device__ __forceinline__ size_t unknown_index(const StageArgs& a, int j) {
 }
 
 // z slots 0 and cnt hold the known end unknowns; fill in the interior ones.
+// ustage: 8 x TRI, scratch: 8 x 64 (both shared)
 __device__ __forceinline__ void chunk_backward(const StageArgs& a, int r0, int cnt, cd* z,
-                                               cd* ustage) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+                                               cd* ustage, cd* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int lam = a.mu - 1; lam >= 0; --lam) {
     const int s = 1 << lam;
     const int ml = (cnt + s - 1) >> lam;
+    const int np = ml / 2;
     const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-    for (int i = warp; i < ml / 2; i += nwarps) {
+    const int gw = group_width(np);
+    const Group grp{warp % gw, warp / gw};
+    const int ngroups = 8 / gw;
+    cd* part = scratch + grp.gid * gw * 2 * SB;
+    cd* ust = ustage + grp.gid * gw * TRI;
+    for (int i = grp.gid; i < np; i += ngroups) {
       const int ql = 2 * i * s, qm = ql + s, qr = min(ql + 2 * s, cnt);
       const size_t gp = pair0 + i;
-      pair_backward(a.pairs + gp * PAIR_STRIDE, a.gvec + gp * SB, z + ql * SB, z + qr * SB,
-                    z + qm * SB, a.xv + unknown_index(a, r0 + qm) * SB, ustage + warp * TRI, lane);
+      const cd* rec = a.pairs + gp * PAIR_STRIDE;
+      const cd* g = a.gvec + gp * SB;
+      cd* xg = a.xv + unknown_index(a, r0 + qm) * SB;
+      if (gw == 1) pair_backward<1>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
+      else if (gw == 2) pair_backward<2>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
+      else if (gw == 4) pair_backward<4>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
+      else pair_backward<8>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
     }
     __syncthreads();
   }
@@ -205,6 +322,7 @@ __global__ void __launch_bounds__(256) slu_fwd_stage_kernel(StageArgs a) {
   cd* scratch = buf1 + C * SB;           // 8 warps x 64
   const int r0 = blockIdx.x * C;
   const int cnt = min(C, a.m0 - r0);
+  prefetch_records(a, r0, cnt, 1, PR_PERM, PR_FWD_END);
   for (int e = threadIdx.x; e < cnt * SB; e += blockDim.x)
     buf0[e] = a.fin[static_cast<size_t>(r0) * SB + e];
   __syncthreads();
@@ -217,33 +335,39 @@ __global__ void __launch_bounds__(256) slu_bwd_stage_kernel(StageArgs a) {
   const int C = 1 << a.mu;
   cd* z = reinterpret_cast<cd*>(smem_raw);   // (C + 1) x 32
   cd* ustage = z + (C + 1) * SB;             // 8 warps x TRI
+  cd* scratch = ustage + 8 * TRI;            // 8 warps x 64
   const int r0 = blockIdx.x * C;
   const int cnt = min(C, a.m0 - r0);
+  prefetch_records(a, r0, cnt, 0, PR_E, PR_U + TRI);
   if (threadIdx.x < SB) z[threadIdx.x] = a.xv[unknown_index(a, r0) * SB + threadIdx.x];
   else if (threadIdx.x < 2 * SB)
     z[cnt * SB + threadIdx.x - SB] = a.xv[unknown_index(a, r0 + cnt) * SB + threadIdx.x - SB];
   __syncthreads();
-  chunk_backward(a, r0, cnt, z, ustage);
+  chunk_backward(a, r0, cnt, z, ustage, scratch);
 }
 
 // Single CTA: remaining levels forward, dense top system, back substitution.
 __global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = 1 << a.mu;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cd* buf0 = reinterpret_cast<cd*>(smem_raw);
   cd* buf1 = buf0 + C * SB;
   cd* z = buf1 + C * SB;                  // (C + 1) x 32
-  cd* tvec = z + (C + 1) * SB;            // 64 permuted rhs + 64 scratch
-  cd* big = tvec + 128;                   // max(8 * TRI, 64 * 64): U of the top system / U stages
+  cd* scratch = z + (C + 1) * SB;         // 8 x 64
+  cd* big = scratch + 8 * 2 * SB;         // max(8 * TRI, 64 * 64 + 64): top U / U stages
   const int cnt = a.m0;
+  const int TS = a.top_size;
+  // everything this CTA will read is static: pull it into L2 up front
+  prefetch_records(a, 0, cnt, 1, PR_PERM, PR_FWD_END);
+  prefetch_records(a, 0, cnt, 0, PR_E, PR_U + TRI);
+  for (int e = tid; e < TOP_STRIDE / 8; e += blockDim.x)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.top + e * 8));
   for (int e = tid; e < cnt * SB; e += blockDim.x) buf0[e] = a.fin[e];
   __syncthreads();
   const cd* res = buf0;
-  if (cnt > 0) res = chunk_forward(a, 0, cnt, buf0, buf1, big /*8 x 64 scratch*/);
+  if (cnt > 0) res = chunk_forward(a, 0, cnt, buf0, buf1, scratch);
   // ---- top system: [boundary row of node 0 ; last reduced row ; boundary row of node n_pad-1]
-  const int TS = a.top_size;
-  __syncthreads();
   cd* t = big + 64 * 64;   // 64 entries behind the staged U
   if (tid < 64) {
     cd v{0.0, 0.0};
@@ -255,28 +379,57 @@ __global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
     }
     t[tid] = v;
   }
-  for (int e = tid; e < 64 * 64; e += blockDim.x) big[e] = a.top[TOP_U + e];
+  for (int e = tid; e < 64 * 64; e += blockDim.x) cp_async16(big + e, a.top + TOP_U + e);
+  cp_async_commit();
   __syncthreads();
-  const uint8_t* perm = reinterpret_cast<const uint8_t*>(a.top);
-  cd y{0.0, 0.0};
-  if (tid < TS) {
+  // y = Linv (P t): 8 warps x 8 columns each, two rows per lane
+  {
+    const uint8_t* perm = reinterpret_cast<const uint8_t*>(a.top);
     const cd* Linv = a.top + TOP_LINV;
-    for (int c = 0; c < TS; ++c) cfma(y, ldg_cd(Linv + c * 64 + tid), t[perm[c]]);
+    cd m0[8], m1[8], p0{0.0, 0.0}, p1{0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      m0[c] = ldg_cd(Linv + (warp * 8 + c) * 64 + lane);
+      m1[c] = ldg_cd(Linv + (warp * 8 + c) * 64 + 32 + lane);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const cd tv = t[perm[warp * 8 + c]];
+      cfma(p0, m0[c], tv);
+      cfma(p1, m1[c], tv);
+    }
+    scratch[warp * 64 + lane] = p0;
+    scratch[warp * 64 + 32 + lane] = p1;
   }
-  __shared__ cd xk_s;
-  for (int k = TS - 1; k >= 0; --k) {
-    if (tid == k) { y = y * big[k * 64 + k]; xk_s = y; }
-    __syncthreads();
-    if (tid < k) cfms(y, big[k * 64 + tid], xk_s);
-    __syncthreads();
-  }
-  if (tid < TS) {
-    const int half = tid >> 5, e = tid & 31;       // half 0: z_0, half 1: z_{K-1}
-    z[(half ? cnt : 0) * SB + e] = y;
-    a.xv[(half ? static_cast<size_t>(a.K - 1) : 0) * SB + e] = y;
+  cp_async_wait_all();
+  __syncthreads();
+  if (warp == 0) {
+    cd y0{0.0, 0.0}, y1{0.0, 0.0};   // rows lane and lane + 32
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { y0 += scratch[w * 64 + lane]; y1 += scratch[w * 64 + 32 + lane]; }
+    // back substitution with U (column-major, ld 64, reciprocal diagonal), one warp
+    for (int k = TS - 1; k >= 0; --k) {
+      const cd* col = big + k * 64;
+      const cd cand = (k >= 32 ? y1 : y0) * col[k];
+      const cd xk = shfl_cd(cand, k & 31);
+      if (k >= 32) {
+        if (lane + 32 < k) cfms(y1, col[lane + 32], xk);
+        else if (lane + 32 == k) y1 = xk;
+        cfms(y0, col[lane], xk);
+      } else {
+        if (lane < k) cfms(y0, col[lane], xk);
+        else if (lane == k) y0 = xk;
+      }
+    }
+    z[lane] = y0;
+    a.xv[lane] = y0;
+    if (TS == 64) {
+      z[cnt * SB + lane] = y1;
+      a.xv[static_cast<size_t>(a.K - 1) * SB + lane] = y1;
+    }
   }
   __syncthreads();
-  if (cnt > 0) chunk_backward(a, 0, cnt, z, big);
+  if (cnt > 0) chunk_backward(a, 0, cnt, z, big, scratch);
 }
 
 // ------------------------------------------------------------------ factorisation kernels
@@ -636,9 +789,9 @@ StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const 
 }
 
 size_t fwd_smem(int mu) { return sizeof(cd) * ((2 << mu) * SB + 8 * 2 * SB); }
-size_t bwd_smem(int mu) { return sizeof(cd) * (((1 << mu) + 1) * SB + 8 * TRI); }
+size_t bwd_smem(int mu) { return sizeof(cd) * (((1 << mu) + 1) * SB + 8 * TRI + 8 * 2 * SB); }
 size_t top_smem(int mu) {
-  return sizeof(cd) * ((2 << mu) * SB + ((1 << mu) + 1) * SB + 128 + 64 * 64 + 64 + 8 * TRI);
+  return sizeof(cd) * ((2 << mu) * SB + ((1 << mu) + 1) * SB + 8 * 2 * SB + 64 * 64 + 64 + 8 * TRI);
 }
 constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + SB * 33 + 64) + sizeof(int) * 64;
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
