@@ -239,7 +239,7 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
 int do_factorize(lgpu_ctx* c, cd sigma) {
   if (!c->assembled()) return fail(c, LGPU_ESTATE, "factorize: matrices not assembled");
   if (c->splan.n != c->G) {
-    c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 4),
+    c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 3),
                              env_int("LGPU_SLU_TOP", 32));
     c->pairs.ensure(std::max<size_t>(c->splan.pair_records, 1) * PAIR_STRIDE);
     c->topfac.ensure(TOP_STRIDE);

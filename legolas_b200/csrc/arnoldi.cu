@@ -24,9 +24,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // true for exactly one CTA: the last one to arrive; its view of global memory then contains
 // every other CTA's partials.
-__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket, bool wrote_partials) {
   __shared__ bool is_last;
-  __threadfence();
+  if (wrote_partials) __threadfence();   // only the threads that published partials need the fence
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int t = atomicAdd(ticket, 1u);
@@ -37,33 +37,59 @@ __device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
   return is_last;
 }
 
+// h = V(:, 0:ncols)^H w.  One thread owns two rows of the tile; columns are processed in
+// chunks of 8 so that 16 independent 16-byte loads per thread are in flight, then the 8 partial
+// dot products are reduced across the CTA (shuffle tree + shared memory).
+constexpr int DOT_CHUNK = 8;
+
 __global__ void __launch_bounds__(256)
 krylov_dots_kernel(int n, const cd* __restrict__ V, int ldv, int ncols, const cd* __restrict__ w,
                    cd* __restrict__ partial, cd* __restrict__ hwork, cd* Hcol, int accumulate,
                    unsigned int* ticket) {
-  __shared__ cd ws[KRYLOV_TILE];
+  __shared__ cd red[8][DOT_CHUNK];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * KRYLOV_TILE;
-  for (int r = tid; r < KRYLOV_TILE; r += 256)
-    ws[r] = (row0 + r < n) ? w[row0 + r] : cd{0.0, 0.0};
-  __syncthreads();
-  for (int c = warp; c < ncols; c += 8) {
-    const cd* col = V + static_cast<size_t>(c) * ldv + row0;
-    cd acc{0.0, 0.0};
-#pragma unroll 8
-    for (int r = lane; r < KRYLOV_TILE; r += 32) {
-      if (row0 + r < n) cfmac(acc, ldg_cd(col + r), ws[r]);
+  const int i0 = row0 + tid, i1 = row0 + 256 + tid;
+  const bool ok0 = i0 < n, ok1 = i1 < n;
+  const cd w0 = ok0 ? w[i0] : cd{0.0, 0.0}, w1 = ok1 ? w[i1] : cd{0.0, 0.0};
+  for (int cb = 0; cb < ncols; cb += DOT_CHUNK) {
+    cd a0[DOT_CHUNK], a1[DOT_CHUNK];
+#pragma unroll
+    for (int c = 0; c < DOT_CHUNK; ++c) {
+      const bool okc = cb + c < ncols;
+      const cd* col = V + static_cast<size_t>(cb + c) * ldv;
+      a0[c] = (okc && ok0) ? ldg_cd(col + i0) : cd{0.0, 0.0};
+      a1[c] = (okc && ok1) ? ldg_cd(col + i1) : cd{0.0, 0.0};
     }
-    acc.x = warp_sum(acc.x);
-    acc.y = warp_sum(acc.y);
-    if (lane == 0) partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + c] = acc;
-  }
-  if (last_block_done(ticket)) {
-    for (int c = tid; c < ncols; c += 256) {
+#pragma unroll
+    for (int c = 0; c < DOT_CHUNK; ++c) {
+      cd acc{0.0, 0.0};
+      cfmac(acc, a0[c], w0);
+      cfmac(acc, a1[c], w1);
+      acc.x = warp_sum(acc.x);
+      acc.y = warp_sum(acc.y);
+      if (lane == 0) red[warp][c] = acc;
+    }
+    __syncthreads();
+    if (tid < DOT_CHUNK && cb + tid < ncols) {
       cd s{0.0, 0.0};
-      for (unsigned int b = 0; b < gridDim.x; ++b) s += partial[static_cast<size_t>(b) * PSTRIDE + c];
-      hwork[c] = s;
-      if (Hcol) Hcol[c] = accumulate ? Hcol[c] + s : s;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][tid];
+      partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + cb + tid] = s;
+    }
+    __syncthreads();
+  }
+  if (last_block_done(ticket, tid < DOT_CHUNK)) {
+    // one warp per column: lanes stride over the CTA partials, fixed-order shuffle tree
+    for (int c = warp; c < ncols; c += 8) {
+      cd s{0.0, 0.0};
+      for (unsigned int b = lane; b < gridDim.x; b += 32) s += partial[static_cast<size_t>(b) * PSTRIDE + c];
+      s.x = warp_sum(s.x);
+      s.y = warp_sum(s.y);
+      if (lane == 0) {
+        hwork[c] = s;
+        if (Hcol) Hcol[c] = accumulate ? Hcol[c] + s : s;
+      }
     }
     if (tid == 0) *ticket = 0u;
   }
@@ -100,13 +126,16 @@ krylov_update_kernel(int n, const cd* __restrict__ V, int ldv, int ncols, cd* __
     for (int k = 0; k < 8; ++k) s += red[k];
     partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + KRYLOV_MAXCOL] = cd{s, 0.0};
   }
-  if (last_block_done(ticket)) {
-    if (tid == 0) {
+  if (last_block_done(ticket, tid == 0)) {
+    if (warp == 0) {
       double s = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b)
+      for (unsigned int b = lane; b < gridDim.x; b += 32)
         s += partial[static_cast<size_t>(b) * PSTRIDE + KRYLOV_MAXCOL].x;
-      scal[0] = sqrt(s);
-      *ticket = 0u;
+      s = warp_sum(s);
+      if (lane == 0) {
+        scal[0] = sqrt(s);
+        *ticket = 0u;
+      }
     }
   }
 }

@@ -102,6 +102,8 @@ struct StageArgs {
 // warp owns a pair, at the narrow upper levels all 8 warps share one so that each lane has
 // only 64 / GW independent 16-byte loads to wait for.  The 32 x 32 matvecs are split by
 // columns across the warps of a group; partial sums meet in shared memory.
+constexpr int LB = 8;   // independent 16-byte loads in flight per lane and batch
+
 struct Group {
   int wg;     // warp index inside the group
   int gid;    // group index inside the CTA (named barrier gid + 1)
@@ -132,16 +134,16 @@ __device__ __forceinline__ void pair_forward(const cd* __restrict__ rec, const c
   const cd* L = rec + PR_L11I;
   cd g{0.0, 0.0};
   {
-    cd m[CW > 16 ? 16 : CW];
+    cd m[CW > LB ? LB : CW];
 #pragma unroll
-    for (int cb = 0; cb < CW; cb += 16) {
+    for (int cb = 0; cb < CW; cb += LB) {
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) {
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) {
         const int col = c0 + cb + c;
         m[c] = lane >= col ? ldg_cd(L + tri_lo_off(col) + lane - col) : cd{0.0, 0.0};
       }
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(g, m[c], shfl_cd(v1, c0 + cb + c));
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(g, m[c], shfl_cd(v1, c0 + cb + c));
     }
   }
   if (GW > 1) {
@@ -155,13 +157,13 @@ __device__ __forceinline__ void pair_forward(const cd* __restrict__ rec, const c
   const cd* M = rec + PR_L21;
   cd acc{0.0, 0.0};
   {
-    cd m[CW > 16 ? 16 : CW];
+    cd m[CW > LB ? LB : CW];
 #pragma unroll
-    for (int cb = 0; cb < CW; cb += 16) {
+    for (int cb = 0; cb < CW; cb += LB) {
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) m[c] = ldg_cd(M + (c0 + cb + c) * SB + lane);
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) m[c] = ldg_cd(M + (c0 + cb + c) * SB + lane);
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(acc, m[c], shfl_cd(g, c0 + cb + c));
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(acc, m[c], shfl_cd(g, c0 + cb + c));
     }
   }
   if (GW > 1) {
@@ -194,17 +196,17 @@ __device__ __forceinline__ void pair_backward(const cd* __restrict__ rec, const 
   const cd* F = rec + PR_F;
   cd acc{0.0, 0.0};
   {
-    cd m[CW > 16 ? 16 : CW];
+    cd m[CW > LB ? LB : CW];
 #pragma unroll
-    for (int cb = 0; cb < CW; cb += 16) {
+    for (int cb = 0; cb < CW; cb += LB) {
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) m[c] = ldg_cd(E + (c0 + cb + c) * SB + lane);
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) m[c] = ldg_cd(E + (c0 + cb + c) * SB + lane);
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(acc, m[c], zl[c0 + cb + c]);
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(acc, m[c], zl[c0 + cb + c]);
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) m[c] = ldg_cd(F + (c0 + cb + c) * SB + lane);
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) m[c] = ldg_cd(F + (c0 + cb + c) * SB + lane);
 #pragma unroll
-      for (int c = 0; c < (CW > 16 ? 16 : CW); ++c) cfma(acc, m[c], zr[c0 + cb + c]);
+      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(acc, m[c], zr[c0 + cb + c]);
     }
   }
   if (GW > 1) part[grp.wg * SB + lane] = acc;
@@ -294,19 +296,18 @@ __device__ __forceinline__ void chunk_backward(const StageArgs& a, int r0, int c
     const int ml = (cnt + s - 1) >> lam;
     const int np = ml / 2;
     const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-    const int gw = group_width(np);
+    const int gw = max(2, group_width(np));
     const Group grp{warp % gw, warp / gw};
     const int ngroups = 8 / gw;
     cd* part = scratch + grp.gid * gw * 2 * SB;
-    cd* ust = ustage + grp.gid * gw * TRI;
+    cd* ust = ustage + grp.gid * TRI;
     for (int i = grp.gid; i < np; i += ngroups) {
       const int ql = 2 * i * s, qm = ql + s, qr = min(ql + 2 * s, cnt);
       const size_t gp = pair0 + i;
       const cd* rec = a.pairs + gp * PAIR_STRIDE;
       const cd* g = a.gvec + gp * SB;
       cd* xg = a.xv + unknown_index(a, r0 + qm) * SB;
-      if (gw == 1) pair_backward<1>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
-      else if (gw == 2) pair_backward<2>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
+      if (gw == 2) pair_backward<2>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
       else if (gw == 4) pair_backward<4>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
       else pair_backward<8>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
     }
@@ -314,7 +315,7 @@ __device__ __forceinline__ void chunk_backward(const StageArgs& a, int r0, int c
   }
 }
 
-__global__ void __launch_bounds__(256) slu_fwd_stage_kernel(StageArgs a) {
+__global__ void __launch_bounds__(256, 3) slu_fwd_stage_kernel(StageArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = 1 << a.mu;
   cd* buf0 = reinterpret_cast<cd*>(smem_raw);
@@ -330,12 +331,12 @@ __global__ void __launch_bounds__(256) slu_fwd_stage_kernel(StageArgs a) {
   if (threadIdx.x < SB) a.fout[static_cast<size_t>(blockIdx.x) * SB + threadIdx.x] = res[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256) slu_bwd_stage_kernel(StageArgs a) {
+__global__ void __launch_bounds__(256, 3) slu_bwd_stage_kernel(StageArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = 1 << a.mu;
   cd* z = reinterpret_cast<cd*>(smem_raw);   // (C + 1) x 32
-  cd* ustage = z + (C + 1) * SB;             // 8 warps x TRI
-  cd* scratch = ustage + 8 * TRI;            // 8 warps x 64
+  cd* ustage = z + (C + 1) * SB;             // 4 groups x TRI
+  cd* scratch = ustage + 4 * TRI;            // 8 warps x 64
   const int r0 = blockIdx.x * C;
   const int cnt = min(C, a.m0 - r0);
   prefetch_records(a, r0, cnt, 0, PR_E, PR_U + TRI);
@@ -789,7 +790,7 @@ StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const 
 }
 
 size_t fwd_smem(int mu) { return sizeof(cd) * ((2 << mu) * SB + 8 * 2 * SB); }
-size_t bwd_smem(int mu) { return sizeof(cd) * (((1 << mu) + 1) * SB + 8 * TRI + 8 * 2 * SB); }
+size_t bwd_smem(int mu) { return sizeof(cd) * (((1 << mu) + 1) * SB + 4 * TRI + 8 * 2 * SB); }
 size_t top_smem(int mu) {
   return sizeof(cd) * ((2 << mu) * SB + ((1 << mu) + 1) * SB + 8 * 2 * SB + 64 * 64 + 64 + 8 * TRI);
 }
