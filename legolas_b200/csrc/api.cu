@@ -93,7 +93,8 @@ struct lgpu_ctx {
 
   // vectors / Krylov storage
   DevBuf<cd> vx, vy, vu, vr, ve;
-  DevBuf<cd> V, resid, Hdev, Qdev, Z, kpartial, khwork;
+  DevBuf<cd> V, vcur, resid, Hdev, Qdev, Z, kpartial, khwork;
+  BasisLayout basis{};
   DevBuf<double> kscal;
   DevBuf<unsigned int> kticket;
   PinnedBuf<cd> h_stage;
@@ -143,7 +144,8 @@ void ensure_vectors(lgpu_ctx* c) {
 }
 
 void ensure_krylov_work(lgpu_ctx* c) {
-  const size_t tiles = (static_cast<size_t>(c->N) + KRYLOV_TILE - 1) / KRYLOV_TILE;
+  // one partial row per tile of the basis (dot / update kernels run one CTA per tile)
+  const size_t tiles = static_cast<size_t>(make_basis_layout(c->N, 1).ntiles);
   c->kpartial.ensure(tiles * (KRYLOV_MAXCOL + 1));
   c->khwork.ensure(KRYLOV_MAXCOL + 1);
   if (!c->kscal.p) {
@@ -248,6 +250,27 @@ int do_factorize(lgpu_ctx* c, cd sigma) {
     c->gvec.ensure(std::max<size_t>(c->splan.pair_records, 1) * SB);
     c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
     c->d_info.ensure(1);
+    // Keep the factor records of the narrow upper levels (latency-bound, ~20 MB at G = 10001)
+    // resident in L2: persisting access-policy window on the context's stream.
+    const int nl = static_cast<int>(c->splan.levels.size());
+    const int lsplit = env_int("LGPU_L2_PERSIST_LEVEL", 4);
+    if (lsplit >= 0 && lsplit < nl) {
+      const size_t first = c->splan.levels[lsplit].off_pairs;
+      const size_t bytes = (c->splan.pair_records - first) * PAIR_STRIDE * sizeof(cd);
+      int dev_max = 0;
+      cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+      if (bytes > 0 && dev_max > 0 && bytes <= static_cast<size_t>(dev_max)) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = c->pairs.p + first * PAIR_STRIDE;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+          cudaGetLastError();   // optional optimisation: ignore if unsupported
+      }
+    }
   }
   ensure_vectors(c);
   c->log.stream = c->stream;
@@ -301,17 +324,18 @@ class CudaKrylovOps final : public KrylovOps {
     const KrylovWork kw = kwork(c_);
     cd* V = c_->V.p;
     cd* H = c_->Hdev.p;
-    if (k == 0) krylov_norm(n, c_->resid.p, kw, c_->stream, &c_->log);
+    const BasisLayout& L = c_->basis;
+    (void)n;
+    if (k == 0) krylov_update(L, V, 0, c_->resid.p, kw, c_->stream, &c_->log);   // rnorm = ||resid||
     for (int j = k; j < m; ++j) {
-      cd* vj = V + static_cast<size_t>(j) * n;
       cd* hsub = j > 0 ? H + static_cast<size_t>(j - 1) * ncv_ + j : nullptr;
-      krylov_scale(n, c_->resid.p, vj, kw, hsub, c_->stream, &c_->log);
-      dev_apply_op(c_, vj, c_->resid.p, refine_);
+      krylov_scale(L, c_->resid.p, V, j, c_->vcur.p, kw, hsub, c_->stream, &c_->log);
+      dev_apply_op(c_, c_->vcur.p, c_->resid.p, refine_);
       cd* hcol = H + static_cast<size_t>(j) * ncv_;
-      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->log);
-      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
-      krylov_dots(n, V, n, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
-      krylov_update(n, V, n, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
+      krylov_dots(L, V, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->log);
+      krylov_update(L, V, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
+      krylov_dots(L, V, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
+      krylov_update(L, V, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
     }
   }
 
@@ -352,10 +376,11 @@ class CudaKrylovOps final : public KrylovOps {
     const int n = c_->N;
     upload_small(Q, ldq, kplusp, kev + 1 <= kplusp ? kev + 1 : kplusp);
     const int nc = kev + 1 <= kplusp ? kev + 1 : kplusp;
-    basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nc, c_->V.p, n, c_->stream, &c_->log);
-    vec_axpby(n, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
-              c_->V.p + static_cast<size_t>(kev) * n, c_->stream, &c_->log);
-    krylov_norm(n, c_->resid.p, kwork(c_), c_->stream, &c_->log);
+    (void)n;
+    basis_gemm(c_->basis, c_->V.p, kplusp, c_->Qdev.p, ncv_, nc, c_->V.p, 0, c_->stream, &c_->log);
+    vec_axpby_basis(c_->basis, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
+                    c_->V.p, kev, c_->stream, &c_->log);
+    krylov_update(c_->basis, c_->V.p, 0, c_->resid.p, kwork(c_), c_->stream, &c_->log);
     // the staging buffer is reused by the next fetch(): make sure the upload has been consumed
     CUDA_CHECK(cudaStreamSynchronize(c_->stream));
   }
@@ -363,7 +388,7 @@ class CudaKrylovOps final : public KrylovOps {
   void ritz_vectors(int kplusp, int nconv, const cplx* S, int lds) override {
     const int n = c_->N;
     upload_small(S, lds, kplusp, nconv);
-    basis_gemm(n, c_->V.p, n, kplusp, c_->Qdev.p, ncv_, nconv, c_->Z.p, n, c_->stream,
+    basis_gemm(c_->basis, c_->V.p, kplusp, c_->Qdev.p, ncv_, nconv, c_->Z.p, n, c_->stream,
                &c_->log);
   }
 
@@ -389,7 +414,9 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   int rc = do_factorize(c, cd{cfg->sigma_re, cfg->sigma_im});
   if (rc != LGPU_OK) return rc;
   const int ncv = cfg->ncv, nev = cfg->nev;
-  c->V.ensure(static_cast<size_t>(n) * ncv);
+  c->basis = make_basis_layout(n, ncv);
+  c->V.ensure(c->basis.elems());
+  c->vcur.ensure(n);
   c->resid.ensure(n);
   c->Hdev.ensure(static_cast<size_t>(ncv) * ncv);
   c->Qdev.ensure(static_cast<size_t>(ncv) * ncv);

@@ -5,6 +5,15 @@
 //
 // Replaces what ARPACK's znaitr / znapps / zneupd do with zgemv / zgemm on the host
 // (arpack-ng, called from src/solvers/arnoldi/smod_arpack_shift_invert.f08:64-81,119-143).
+//
+// Basis layout.  ARPACK keeps V column-major (N x ncv).  On HBM that makes every CTA of a
+// tall-skinny kernel read ncv short streams 16*N bytes apart (hundreds of concurrent DRAM
+// streams, ~25 % of the copy bandwidth measured).  Here V is tiled by rows: tile t holds
+// rows [t*T, (t+1)*T) of ALL columns contiguously,
+//       V(i, c)  at  ((i / T) * ncv + c) * T + i % T ,
+// so a CTA that owns a tile streams one contiguous T*ncv*16-byte region; T is chosen so that
+// there is one tile per SM and the CTA has T/2 threads (two rows per thread, equal work).  Only the library sees this layout: start vector, operator
+// input and Ritz vectors are plain contiguous vectors.
 #pragma once
 
 #include <cstdint>
@@ -13,11 +22,21 @@
 
 namespace lgpu {
 
-constexpr int KRYLOV_TILE = 512;     // rows per CTA in the dot / update kernels
 constexpr int KRYLOV_MAXCOL = 128;   // ncv limit of the device kernels
+constexpr int KRYLOV_MAX_T = 1280;   // rows per tile (two rows per thread, <= 640 threads)
+
+struct BasisLayout {
+  int n;        // rows
+  int ncv;      // columns stored per tile
+  int T;        // rows per tile (multiple of 32)
+  int ntiles;
+  size_t elems() const { return static_cast<size_t>(ntiles) * ncv * T; }
+};
+
+BasisLayout make_basis_layout(int n, int ncv);
 
 struct KrylovWork {
-  cd* partial;        // [max_ctas][KRYLOV_MAXCOL + 1]
+  cd* partial;        // [ntiles][KRYLOV_MAXCOL + 1]
   cd* hwork;          // [KRYLOV_MAXCOL + 1] coefficients of the current projection
   double* scal;       // [0] rnorm  [1] scratch
   unsigned int* ticket;
@@ -25,22 +44,23 @@ struct KrylovWork {
 
 // h = V(:, 0:ncols)^H w  -> work.hwork ; Hcol (device, may be null) gets `=` (accumulate == 0)
 // or `+=` (accumulate == 1).
-void krylov_dots(int n, const cd* V, int ldv, int ncols, const cd* w, const KrylovWork& work,
+void krylov_dots(const BasisLayout& L, const cd* V, int ncols, const cd* w, const KrylovWork& work,
                  cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log);
-// w -= V(:, 0:ncols) hwork ; afterwards scal[0] = ||w||_2
-void krylov_update(int n, const cd* V, int ldv, int ncols, cd* w, const KrylovWork& work,
+// w -= V(:, 0:ncols) hwork ; afterwards scal[0] = ||w||_2   (ncols == 0: just the norm)
+void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const KrylovWork& work,
                    cudaStream_t stream, LaunchLog* log);
-// scal[0] = ||w||_2
-void krylov_norm(int n, const cd* w, const KrylovWork& work, cudaStream_t stream,
-                 LaunchLog* log);
-// vout = w / scal[0] ; if hsub != null: *hsub = (scal[0], 0)
-void krylov_scale(int n, const cd* w, cd* vout, const KrylovWork& work, cd* hsub,
-                  cudaStream_t stream, LaunchLog* log);
+// V(:, col) = vplain = w / scal[0] ; if hsub != null: *hsub = (scal[0], 0)
+void krylov_scale(const BasisLayout& L, const cd* w, cd* V, int col, cd* vplain,
+                  const KrylovWork& work, cd* hsub, cudaStream_t stream, LaunchLog* log);
 // Out(:, 0:nc) = V(:, 0:nk) Q(0:nk, 0:nc); Q is a device matrix with leading dimension ldq.
-// Out may alias V (row-local update).
-void basis_gemm(int n, const cd* V, int ldv, int nk, const cd* Q, int ldq, int nc, cd* Out,
-                int ldo, cudaStream_t stream, LaunchLog* log);
-// r = a*r + b*v
+// out_plain_ld == 0: Out is a tiled basis (may alias V: the update is row-local);
+// otherwise Out is plain column-major with that leading dimension.
+void basis_gemm(const BasisLayout& L, const cd* V, int nk, const cd* Q, int ldq, int nc, cd* Out,
+                int out_plain_ld, cudaStream_t stream, LaunchLog* log);
+// r = a*r + b*V(:, col)
+void vec_axpby_basis(const BasisLayout& L, cd a, cd* r, cd b, const cd* V, int col,
+                     cudaStream_t stream, LaunchLog* log);
+// r = a*r + b*v (plain vectors)
 void vec_axpby(int n, cd a, cd* r, cd b, const cd* v, cudaStream_t stream, LaunchLog* log);
 
 }  // namespace lgpu
