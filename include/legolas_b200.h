@@ -22,6 +22,7 @@
 #ifndef LEGOLAS_B200_H
 #define LEGOLAS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -152,6 +153,12 @@ int lgpu_shift_invert(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resi
  * (used for device-resident timing and for chaining into device-side consumers). */
 int lgpu_shift_invert_device(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_dev,
                              double* omega_ri_host, double* vr_dev, lgpu_stats* stats);
+
+/* Page-locked host memory for callers that want the eigenvector read-back (N x nev complex,
+ * 51 MB at the headline size) at full PCIe speed instead of the pageable-memory staging path.
+ * Any host pointer is accepted by every entry point; these are optional. */
+void* lgpu_host_alloc(size_t bytes);
+void lgpu_host_free(void* ptr);
 
 /* Host utility: LAPACK zlarnv(idist=2) (uniform (-1,1) re and im), bit-exact port of
  * dlaruv's 48-bit multiplicative congruential generator; iseed[4] updated in place. */

@@ -350,15 +350,29 @@ class Context:
 
     # ---- the eigen-solve
     def shift_invert(self, cfg: ArpackConfig, sigma: complex, refine_steps: int = 0,
-                     want_vectors: bool = True):
+                     want_vectors: bool = True, vr_view: bool = False):
+        """``vr_view=True`` returns the Ritz vectors as a view of the context's page-locked
+        read-back buffer (valid until the next solve on this context) instead of a copy."""
         ca = _arnoldi_c(cfg, sigma, refine_steps)
         resid = np.ascontiguousarray(cfg.residual, dtype=np.complex128)
         omega = np.empty(cfg.nev, dtype=np.complex128)
-        vr = np.empty((cfg.evpdim, cfg.nev), dtype=np.complex128, order="F") if want_vectors else None
+        vr = None
+        if want_vectors:
+            nbytes = cfg.evpdim * cfg.nev * 16
+            # reuse one page-locked buffer per context for large read-backs
+            if nbytes >= (1 << 20):
+                if getattr(self, "_vr_pinned", None) is None or self._vr_pinned.shape != (cfg.evpdim, cfg.nev):
+                    self._vr_pinned = pinned_empty((cfg.evpdim, cfg.nev))
+                vr = self._vr_pinned
+            else:
+                vr_view = True
+                vr = np.empty((cfg.evpdim, cfg.nev), dtype=np.complex128, order="F")
         st = CStats()
         self._check(self._lib.lgpu_shift_invert(
             self._h, C.byref(ca), resid.ctypes.data, omega.ctypes.data,
             vr.ctypes.data if vr is not None else None, C.byref(st)), "shift_invert")
+        if vr is not None and not vr_view:
+            vr = np.array(vr, order="F")
         return omega, vr, _stats_dict(st)
 
     def shift_invert_device(self, cfg: ArpackConfig, sigma: complex, resid_ptr: int, vr_ptr: int,
@@ -370,6 +384,39 @@ class Context:
             self._h, C.byref(ca), C.c_void_p(resid_ptr), omega.ctypes.data,
             C.c_void_p(vr_ptr) if vr_ptr else None, C.byref(st)), "shift_invert_device")
         return omega, _stats_dict(st)
+
+
+class _PinnedBlock:
+    """Owner of one page-locked host allocation (freed when the last array view dies)."""
+
+    def __init__(self, lib, nbytes: int):
+        self._lib = lib
+        self.ptr = lib.lgpu_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("lgpu_host_alloc failed")
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            self._lib.lgpu_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.complex128, order="F") -> np.ndarray:
+    """numpy array backed by page-locked memory (fast device -> host copies)."""
+    lib = _lib.load()
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape))
+    block = _PinnedBlock(lib, max(count * dt.itemsize, 1))
+    buf = (C.c_char * block.nbytes).from_address(block.ptr)
+    arr = np.frombuffer(buf, dtype=dt, count=count).reshape(shape, order=order)
+    _PINNED_OWNERS[id(buf)] = block          # keep the allocation alive with the buffer object
+    buf._owner = block
+    return arr
+
+
+_PINNED_OWNERS = {}
 
 
 def _which(which: str) -> int:
@@ -412,7 +459,7 @@ def build_matrices(settings: Settings, grid: np.ndarray, gauss_grid: np.ndarray,
     return Matrices(ctx=ctx, settings=settings)
 
 
-def solve_evp(matrices: Matrices, settings: Settings):
+def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
     """``call solve_evp(matrix_A, matrix_B, settings, omega, right_eigenvectors)`` for
     ``solver = "arnoldi"``, ``arpack_mode = "shift-invert"``.  Returns (omega, vr, arpack_cfg, stats);
     omega(nconv:) is NaN when ARPACK-style convergence was not reached for all nev (a warning,
@@ -426,7 +473,7 @@ def solve_evp(matrices: Matrices, settings: Settings):
     if math.isnan(sv.sigma.real) or math.isnan(sv.sigma.imag):
         raise LegolasError("sigma is not set")
     cfg = new_arpack_config(matrices.ctx.dim, mode=2, bmat="I", solver_settings=sv)
-    omega, vr, stats = matrices.ctx.shift_invert(cfg, complex(sv.sigma), sv.refine_steps)
+    omega, vr, stats = matrices.ctx.shift_invert(cfg, complex(sv.sigma), sv.refine_steps, vr_view=vr_view)
     cfg.info = stats["info"]
     cfg.iparam.update({5: stats["nconv"], 9: stats["n_op"], 10: stats["n_bx"], 11: stats["n_reorth"]})
     return omega, vr, cfg, stats

@@ -17,7 +17,7 @@ HEADERS = ["common.cuh", "assemble.cuh", "slu.cuh", "arnoldi.cuh", "iram.hpp", "
            "terms.def", os.path.join("..", "..", "include", "legolas_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC,-fcx-limited-range",
 ]
 
 

@@ -768,6 +768,19 @@ int lgpu_shift_invert_device(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const doubl
   });
 }
 
+void* lgpu_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes > 0 ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void lgpu_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
 int lgpu_zlarnv(int32_t iseed[4], int32_t n, double* out_ri) {
   if (!iseed || n < 0 || (n > 0 && !out_ri)) return LGPU_EINVAL;
   // LAPACK dlaruv: x_i = seed * a^i mod 2^48, a = 33952834046453, 128 numbers per call;

@@ -12,8 +12,11 @@
 // issued to the device without host synchronisation.
 #pragma once
 
+#include <chrono>
 #include <cmath>
 #include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <limits>
 #include <vector>
@@ -73,6 +76,10 @@ class Iram {
     std::vector<cplx> ritz(kplusp), bounds(kplusp), ritz0(kplusp), bounds0(kplusp);
     std::vector<cplx> Q(static_cast<size_t>(ld) * ld), T(static_cast<size_t>(ld) * ld);
 
+    using clk = std::chrono::steady_clock;
+    auto since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+    double t_enq = 0, t_wait = 0, t_dense = 0, t_compress = 0;
+    const bool trace = std::getenv("LGPU_TRACE") != nullptr;
     ops.init_residual();
     res.n_op = 1;
     int nev = nev0, np = np0;
@@ -82,8 +89,13 @@ class Iram {
     bool first = true;
     while (true) {
       ++iter;
+      auto t0 = clk::now();
       ops.extend(kcur, kplusp);
+      t_enq += since(t0);
+      t0 = clk::now();
       ops.fetch(kcur, kplusp, H_.data(), ld, &rnorm);
+      t_wait += since(t0);
+      t0 = clk::now();
       if (first) {
         first = false;
         if (!(H0norm_ok(rnorm))) { res.info = -9; return res; }
@@ -122,9 +134,15 @@ class Iram {
       cplx sigmak;
       double betak;
       napps(kplusp, nev, np, ritz.data(), Q, &sigmak, &betak);
+      t_dense += since(t0);
+      t0 = clk::now();
       ops.compress(kplusp, nev, Q.data(), ld, sigmak, betak);
+      t_compress += since(t0);
       kcur = nev;
     }
+    if (trace)
+      std::fprintf(stderr, "[lgpu] iram: enqueue %.2f ms, wait %.2f ms, host dense %.2f ms, compress %.2f ms, restarts %d\n",
+                   t_enq, t_wait, t_dense, t_compress, iter);
     res.n_iter = iter;
     res.nconv = std::min(nconv, nev0);
     extract(ops, cfg, kplusp, nev0, np0, res.nconv, tol, eps23, rnorm, ritz0, bounds0, T, Q, res);
