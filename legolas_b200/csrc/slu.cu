@@ -2,6 +2,7 @@
 #include "slu.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace lgpu {
 
@@ -97,185 +98,193 @@ struct StageArgs {
   cd* xv;            // solution, K x 32
 };
 
-// ---- cooperative pair operations ----------------------------------------------------------
-// A pair is processed by a group of GW warps (GW = 1, 2, 4, 8): at the wide lower levels every
-// warp owns a pair, at the narrow upper levels all 8 warps share one so that each lane has
-// only 64 / GW independent 16-byte loads to wait for.  The 32 x 32 matvecs are split by
-// columns across the warps of a group; partial sums meet in shared memory.
-constexpr int LB = 8;   // independent 16-byte loads in flight per lane and batch
+// ---- solve kernels ---------------------------------------------------------------------------
+// A CTA reduces a chunk of 2^mu rows level by level.  The factor records a chunk needs do not
+// depend on the right-hand side, only the order in which they are used does, so a producer
+// warp streams them with cp.async.bulk (TMA) into shared-memory rings as fast as slots are
+// released and the 8 consumer warps find every record already on chip: a level costs its
+// arithmetic, not an HBM round trip per batch of columns.
+//   block ring   16 KB slots, granules in order of use: forward [perm | L11^-1], [L21] per pair,
+//                backward [E], [F] per pair; all 8 warps share one granule (4 columns each)
+//   U ring       8.25 KB slots, one per pair of the backward sweep; up to min(8, nu) pairs of a
+//                level are first reduced to their right-hand sides r = g - E z_l - F z_r (all
+//                warps, pair after pair), then solved at the same time, one warp per pair
+// Every consumer warp acquires and releases every granule of the block ring in order (a warp
+// that skipped a use of a slot could not tell that use from the one after next by the
+// barrier's phase parity); a U slot is waited on by its solver warp only, and two consecutive
+// uses of it are always separated by a CTA-wide barrier.
+constexpr int GRAN = SB2;             // complex entries per block-ring slot
+constexpr int RING_THREADS = 288;     // warps 0-7 consume, warp 8 produces
+constexpr int NCW = 8;                // consumer warps
+constexpr int CW = SB / NCW;          // columns of a 32 x 32 block per warp
+constexpr int BAR_CONSUMERS = 1;      // named barrier over the 256 consumer threads
 
-struct Group {
-  int wg;     // warp index inside the group
-  int gid;    // group index inside the CTA (named barrier gid + 1)
+struct Ring {
+  cd* slots;
+  uint64_t* full;
+  uint64_t* empty;
+  int ns;       // slots
+  int stride;   // complex entries per slot
+};
+struct RingPos {   // next use: slot and its phase parity
+  int slot;
+  uint32_t phase;
 };
 
-template <int GW>
-__device__ __forceinline__ void group_sync(const Group& g) {
-  if (GW == 1) __syncwarp();
-  else asm volatile("bar.sync %0, %1;" ::"r"(g.gid + 1), "r"(GW * 32) : "memory");
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t addr = smem_u32(b);
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 " selp.b32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR_CONSUMERS), "n"(NCW * 32) : "memory");
+}
+__device__ __forceinline__ void advance(const Ring& rg, RingPos& p) {
+  if (++p.slot == rg.ns) { p.slot = 0; p.phase ^= 1u; }
+}
+
+// thread 0, before the CTA-wide barrier that precedes any use
+__device__ __forceinline__ void ring_init(const Ring& rg, int consumers) {
+  for (int i = 0; i < rg.ns; ++i) {
+    mbar_init(&rg.full[i], 1);
+    mbar_init(&rg.empty[i], consumers);
+  }
+}
+__device__ __forceinline__ void ring_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ const cd* ring_acquire(const Ring& rg, const RingPos& p) {
+  mbar_wait(&rg.full[p.slot], p.phase);
+  return rg.slots + p.slot * rg.stride;
+}
+__device__ __forceinline__ void ring_release(const Ring& rg, RingPos& p, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&rg.empty[p.slot]);
+  advance(rg, p);
+}
+// producer lane: next slot of the ring <- `count` complex entries at src.  `p.phase` is the
+// parity of the use being filled; `wrapped` says whether the slot has been used before.
+__device__ __forceinline__ void ring_emit(const Ring& rg, RingPos& p, bool& wrapped, const cd* src,
+                                          int count) {
+  if (wrapped) mbar_wait(&rg.empty[p.slot], p.phase ^ 1u);
+  const uint32_t bytes = static_cast<uint32_t>(count * sizeof(cd));
+  mbar_expect_tx(&rg.full[p.slot], bytes);
+  bulk_g2s(rg.slots + p.slot * rg.stride, src, bytes, &rg.full[p.slot]);
+  if (p.slot == rg.ns - 1) wrapped = true;
+  advance(rg, p);
+}
+
+struct Producer {
+  RingPos blk{0, 0u}, u{0, 0u};
+  bool blk_wrapped = false, u_wrapped = false;
+};
+
+template <bool FWD>
+__device__ __forceinline__ void ring_produce(const StageArgs& a, const Ring& rg, const Ring& ur,
+                                             Producer& pr, int r0, int cnt) {
+  for (int step = 0; step < a.mu; ++step) {
+    const int lam = FWD ? step : a.mu - 1 - step;
+    const int ml = (cnt + (1 << lam) - 1) >> lam;
+    const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
+    for (int i = 0; i < ml / 2; ++i) {
+      const cd* rec = a.pairs + (pair0 + i) * PAIR_STRIDE;
+      if (FWD) {
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_PERM, PR_L21 - PR_PERM);
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_L21, SB2);
+      } else {
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_E, SB2);
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_F, SB2);
+        ring_emit(ur, pr.u, pr.u_wrapped, rec + PR_U, TRI);
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ cd shfl_cd(cd v, int src) {
   return cd{__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)};
 }
 
-// Forward sweep of one merged pair.
+// Forward sweep of one merged pair (all consumer warps).
 //   s: the two stacked right-hand sides (64, shared) ; out: reduced right-hand side (32, shared)
 //   g = L11^-1 (P s)_1  is kept for the back substitution ; out = (P s)_2 - L21 g
-//   part: GW x 32 partial sums (shared, private to the group)
-template <int GW>
-__device__ __forceinline__ void pair_forward(const cd* __restrict__ rec, const cd* s, cd* out,
-                                             cd* __restrict__ gout, cd* part, const Group& grp,
-                                             int lane) {
-  constexpr int CW = SB / GW;   // columns per warp
-  const uint8_t* perm = reinterpret_cast<const uint8_t*>(rec + PR_PERM);
+//   part: 2 x NCW x 32 partial sums
+__device__ __forceinline__ void pair_forward(const Ring& rg, RingPos& pos, const cd* s, cd* out,
+                                             cd* __restrict__ gout, cd* part, int warp, int lane) {
+  const int c0 = warp * CW;
+  const cd* g0 = ring_acquire(rg, pos);
+  const uint8_t* perm = reinterpret_cast<const uint8_t*>(g0 + PR_PERM);
   const cd v1 = s[perm[lane]], v2 = s[perm[SB + lane]];
-  const int c0 = grp.wg * CW;
-  const cd* L = rec + PR_L11I;
-  cd g{0.0, 0.0};
-  {
-    cd m[CW > LB ? LB : CW];
+  const cd* L = g0 + PR_L11I;
+  cd ga{0.0, 0.0}, gb{0.0, 0.0};
 #pragma unroll
-    for (int cb = 0; cb < CW; cb += LB) {
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) {
-        const int col = c0 + cb + c;
-        m[c] = lane >= col ? ldg_cd(L + tri_lo_off(col) + lane - col) : cd{0.0, 0.0};
-      }
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(g, m[c], shfl_cd(v1, c0 + cb + c));
-    }
+  for (int c = 0; c < CW; c += 2) {
+    const int col = c0 + c;
+    const cd ma = lane >= col ? L[tri_lo_off(col) + lane - col] : cd{0.0, 0.0};
+    const cd mb = lane >= col + 1 ? L[tri_lo_off(col + 1) + lane - col - 1] : cd{0.0, 0.0};
+    cfma(ga, ma, shfl_cd(v1, col));
+    cfma(gb, mb, shfl_cd(v1, col + 1));
   }
-  if (GW > 1) {
-    part[grp.wg * SB + lane] = g;
-    group_sync<GW>(grp);
-    g = cd{0.0, 0.0};
+  ring_release(rg, pos, lane);
+  part[warp * SB + lane] = ga + gb;
+  consumer_sync();
+  cd g = part[lane], g2 = part[SB + lane];
 #pragma unroll
-    for (int w = 0; w < GW; ++w) g += part[w * SB + lane];
-    group_sync<GW>(grp);
+  for (int w = 2; w < NCW; w += 2) { g += part[w * SB + lane]; g2 += part[(w + 1) * SB + lane]; }
+  g += g2;
+  const cd* M = ring_acquire(rg, pos);
+  cd aa{0.0, 0.0}, ab{0.0, 0.0};
+#pragma unroll
+  for (int c = 0; c < CW; c += 2) {
+    cfma(aa, M[(c0 + c) * SB + lane], shfl_cd(g, c0 + c));
+    cfma(ab, M[(c0 + c + 1) * SB + lane], shfl_cd(g, c0 + c + 1));
   }
-  const cd* M = rec + PR_L21;
-  cd acc{0.0, 0.0};
-  {
-    cd m[CW > LB ? LB : CW];
+  ring_release(rg, pos, lane);
+  part[(NCW + warp) * SB + lane] = aa + ab;
+  consumer_sync();
+  if (warp == 0) {
+    cd acc = part[NCW * SB + lane], acc2 = part[(NCW + 1) * SB + lane];
 #pragma unroll
-    for (int cb = 0; cb < CW; cb += LB) {
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) m[c] = ldg_cd(M + (c0 + cb + c) * SB + lane);
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(acc, m[c], shfl_cd(g, c0 + cb + c));
-    }
-  }
-  if (GW > 1) {
-    part[grp.wg * SB + lane] = acc;
-    group_sync<GW>(grp);
-    if (grp.wg == 0) {
-      acc = cd{0.0, 0.0};
-#pragma unroll
-      for (int w = 0; w < GW; ++w) acc += part[w * SB + lane];
-    }
-  }
-  if (grp.wg == 0) {
-    out[lane] = v2 - acc;
+    for (int w = 2; w < NCW; w += 2) { acc += part[(NCW + w) * SB + lane]; acc2 += part[(NCW + w + 1) * SB + lane]; }
+    out[lane] = v2 - (acc + acc2);
     gout[lane] = g;
-  }
-  group_sync<GW>(grp);
-}
-
-// Back substitution of one merged pair:  z = U^-1 (g - E z_left - F z_right)
-template <int GW>
-__device__ __forceinline__ void pair_backward(const cd* __restrict__ rec, const cd* __restrict__ g,
-                                              const cd* zl, const cd* zr, cd* zout,
-                                              cd* __restrict__ xg, cd* ustage, cd* part,
-                                              const Group& grp, int lane) {
-  constexpr int CW = SB / GW;
-  for (int e = grp.wg * 32 + lane; e < TRI; e += GW * 32) cp_async16(ustage + e, rec + PR_U + e);
-  cp_async_commit();
-  const int c0 = grp.wg * CW;
-  const cd* E = rec + PR_E;
-  const cd* F = rec + PR_F;
-  cd acc{0.0, 0.0};
-  {
-    cd m[CW > LB ? LB : CW];
-#pragma unroll
-    for (int cb = 0; cb < CW; cb += LB) {
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) m[c] = ldg_cd(E + (c0 + cb + c) * SB + lane);
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(acc, m[c], zl[c0 + cb + c]);
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) m[c] = ldg_cd(F + (c0 + cb + c) * SB + lane);
-#pragma unroll
-      for (int c = 0; c < (CW > LB ? LB : CW); ++c) cfma(acc, m[c], zr[c0 + cb + c]);
-    }
-  }
-  if (GW > 1) part[grp.wg * SB + lane] = acc;
-  cp_async_wait_all();
-  group_sync<GW>(grp);
-  if (grp.wg == 0) {
-    if (GW > 1) {
-      acc = cd{0.0, 0.0};
-#pragma unroll
-      for (int w = 0; w < GW; ++w) acc += part[w * SB + lane];
-    }
-    cd r = g[lane] - acc;
-#pragma unroll 4
-    for (int k = SB - 1; k >= 0; --k) {
-      const int off = tri_up_off(k);
-      const cd xk = shfl_cd(r * ustage[off + k], k);   // diagonal holds 1 / U_kk
-      if (lane < k) cfms(r, ustage[off + lane], xk);
-      else if (lane == k) r = xk;
-    }
-    zout[lane] = r;
-    xg[lane] = r;
-  }
-  group_sync<GW>(grp);
-}
-
-// warps per pair for a level with np pairs in the chunk (8 warps per CTA)
-__device__ __forceinline__ int group_width(int np) { return np >= 5 ? 1 : (np >= 3 ? 2 : (np == 2 ? 4 : 8)); }
-
-// Pull the factor records a chunk will need at its upper levels into L2 while the first
-// level streams from HBM (the records do not depend on the right-hand side).
-__device__ __forceinline__ void prefetch_records(const StageArgs& a, int r0, int cnt, int lam0,
-                                                 int first, int last) {
-  for (int lam = lam0; lam < a.mu; ++lam) {
-    const int ml = (cnt + (1 << lam) - 1) >> lam;
-    const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-    const int lines = (last - first) / 8;   // 128-byte lines per record part
-    for (int e = threadIdx.x; e < (ml / 2) * lines; e += blockDim.x) {
-      const cd* p = a.pairs + (pair0 + e / lines) * PAIR_STRIDE + first + (e % lines) * 8;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
   }
 }
 
 // Reduce the `cnt` rows of a chunk (first row r0 of level l0) to one row; returns the buffer
 // holding it.  Rows merge pairwise, an odd last row is carried up unchanged.
-__device__ __forceinline__ cd* chunk_forward(const StageArgs& a, int r0, int cnt, cd* cur, cd* nxt,
-                                             cd* scratch) {
+__device__ __forceinline__ cd* chunk_forward(const StageArgs& a, const Ring& rg, RingPos& pos, int r0,
+                                             int cnt, cd* cur, cd* nxt, cd* part) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int lam = 0; lam < a.mu; ++lam) {
     const int ml = (cnt + (1 << lam) - 1) >> lam;        // rows of the chunk at this level
     const int np = ml / 2;
     const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-    const int gw = group_width(np);
-    const Group grp{warp % gw, warp / gw};
-    const int ngroups = 8 / gw;
-    cd* part = scratch + grp.gid * gw * 2 * SB;
-    for (int i = grp.gid; i < np; i += ngroups) {
-      const size_t gp = pair0 + i;
-      const cd* rec = a.pairs + gp * PAIR_STRIDE;
-      const cd* s = cur + 2 * i * SB;
-      cd* out = nxt + i * SB;
-      cd* gout = a.gvec + gp * SB;
-      if (gw == 1) pair_forward<1>(rec, s, out, gout, part, grp, lane);
-      else if (gw == 2) pair_forward<2>(rec, s, out, gout, part, grp, lane);
-      else if (gw == 4) pair_forward<4>(rec, s, out, gout, part, grp, lane);
-      else pair_forward<8>(rec, s, out, gout, part, grp, lane);
-    }
-    if ((ml & 1) && warp == 7) nxt[np * SB + lane] = cur[2 * np * SB + lane];
-    __syncthreads();
+    for (int i = 0; i < np; ++i)
+      pair_forward(rg, pos, cur + 2 * i * SB, nxt + i * SB, a.gvec + (pair0 + i) * SB, part, warp, lane);
+    if ((ml & 1) && warp == NCW - 1) nxt[np * SB + lane] = cur[2 * np * SB + lane];
+    consumer_sync();
     cd* t = cur; cur = nxt; nxt = t;
   }
   return cur;
@@ -286,90 +295,192 @@ __device__ __forceinline__ size_t unknown_index(const StageArgs& a, int j) {
   return j < a.m0 ? (static_cast<size_t>(j) << a.l0) : static_cast<size_t>(a.K - 1);
 }
 
+// Unit upper triangular solve by one warp: lane i holds r_i and leaves with x_i.  U is packed by
+// columns with rows already divided by their diagonal entry; the diagonal slot holds 1 / U_ii.
+__device__ __forceinline__ cd unit_upper_solve(const cd* U, cd r, int lane) {
+  r = r * U[tri_up_off(lane) + lane];
+  cd u[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) u[j] = U[tri_up_off(SB - 1 - j) + min(lane, SB - 1 - j)];
+#pragma unroll
+  for (int k = SB - 1; k >= 1; --k) {
+    const cd xk = shfl_cd(r, k);
+    const cd uk = u[(SB - 1 - k) & 3];
+    if (k >= 5) u[(SB - 1 - k) & 3] = U[tri_up_off(k - 4) + min(lane, k - 4)];
+    if (lane < k) cfms(r, uk, xk);
+  }
+  return r;
+}
+
 // z slots 0 and cnt hold the known end unknowns; fill in the interior ones.
-// ustage: 8 x TRI, scratch: 8 x 64 (both shared)
-__device__ __forceinline__ void chunk_backward(const StageArgs& a, int r0, int cnt, cd* z,
-                                               cd* ustage, cd* scratch) {
+//   z = U^-1 (g - E z_left - F z_right) per merged pair, upper levels first
+__device__ __forceinline__ void chunk_backward(const StageArgs& a, const Ring& rg, RingPos& pos,
+                                               const Ring& ur, RingPos& upos, int r0, int cnt, cd* z,
+                                               cd* part) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = warp * CW;
+  const int batch = min(NCW, ur.ns);
+  int flip = 0;
   for (int lam = a.mu - 1; lam >= 0; --lam) {
     const int s = 1 << lam;
     const int ml = (cnt + s - 1) >> lam;
     const int np = ml / 2;
     const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-    const int gw = max(2, group_width(np));
-    const Group grp{warp % gw, warp / gw};
-    const int ngroups = 8 / gw;
-    cd* part = scratch + grp.gid * gw * 2 * SB;
-    cd* ust = ustage + grp.gid * TRI;
-    for (int i = grp.gid; i < np; i += ngroups) {
-      const int ql = 2 * i * s, qm = ql + s, qr = min(ql + 2 * s, cnt);
-      const size_t gp = pair0 + i;
-      const cd* rec = a.pairs + gp * PAIR_STRIDE;
-      const cd* g = a.gvec + gp * SB;
-      cd* xg = a.xv + unknown_index(a, r0 + qm) * SB;
-      if (gw == 2) pair_backward<2>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
-      else if (gw == 4) pair_backward<4>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
-      else pair_backward<8>(rec, g, z + ql * SB, z + qr * SB, z + qm * SB, xg, ust, part, grp, lane);
+    for (int i0 = 0; i0 < np; i0 += batch) {
+      const int nb = min(batch, np - i0);
+      const bool solver = warp < nb;
+      cd r{0.0, 0.0};
+      if (solver) r = a.gvec[(pair0 + i0 + warp) * SB + lane];   // in flight during the matvecs
+      RingPos mine{0, 0u};
+      for (int j = 0; j < nb; ++j) {
+        const int ql = 2 * (i0 + j) * s, qr = min(ql + 2 * s, cnt);
+        const cd* zl = z + ql * SB;
+        const cd* zr = z + qr * SB;
+        cd ae{0.0, 0.0}, af{0.0, 0.0};
+        const cd* E = ring_acquire(rg, pos);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) cfma(ae, E[(c0 + c) * SB + lane], zl[c0 + c]);
+        ring_release(rg, pos, lane);
+        const cd* F = ring_acquire(rg, pos);
+#pragma unroll
+        for (int c = 0; c < CW; ++c) cfma(af, F[(c0 + c) * SB + lane], zr[c0 + c]);
+        ring_release(rg, pos, lane);
+        cd* pj = part + flip * NCW * SB;
+        flip ^= 1;
+        pj[warp * SB + lane] = ae + af;
+        if (j == warp) mine = upos;
+        advance(ur, upos);
+        consumer_sync();
+        if (j == warp) {
+          cd acc = pj[lane], acc2 = pj[SB + lane];
+#pragma unroll
+          for (int w = 2; w < NCW; w += 2) { acc += pj[w * SB + lane]; acc2 += pj[(w + 1) * SB + lane]; }
+          r = r - (acc + acc2);
+        }
+      }
+      if (solver) {
+        mbar_wait(&ur.full[mine.slot], mine.phase);
+        r = unit_upper_solve(ur.slots + mine.slot * ur.stride, r, lane);
+        const int qm = 2 * (i0 + warp) * s + s;
+        z[qm * SB + lane] = r;
+        a.xv[unknown_index(a, r0 + qm) * SB + lane] = r;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ur.empty[mine.slot]);
+      }
+      consumer_sync();
     }
-    __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(256, 3) slu_fwd_stage_kernel(StageArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// shared-memory carve-up helpers (all kernels: block ring first, 128-byte aligned)
+struct SmemCursor {
+  unsigned char* p;
+  template <typename T>
+  __device__ T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(p);
+    p += n * sizeof(T);
+    return r;
+  }
+};
+
+// smem: [ns slots][buf0 C x 32][buf1 C x 32][part 2 x NCW x 32][2 ns barriers]
+__global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArgs a, int ns) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = 1 << a.mu;
-  cd* buf0 = reinterpret_cast<cd*>(smem_raw);
-  cd* buf1 = buf0 + C * SB;
-  cd* scratch = buf1 + C * SB;           // 8 warps x 64
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
+  cd* buf0 = sc.take<cd>(C * SB);
+  cd* buf1 = sc.take<cd>(C * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);
+  uint64_t* bars = sc.take<uint64_t>(2 * ns);
+  const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init_fence(); }
+  __syncthreads();
   const int r0 = blockIdx.x * C;
   const int cnt = min(C, a.m0 - r0);
-  prefetch_records(a, r0, cnt, 1, PR_PERM, PR_FWD_END);
-  for (int e = threadIdx.x; e < cnt * SB; e += blockDim.x)
-    buf0[e] = a.fin[static_cast<size_t>(r0) * SB + e];
-  __syncthreads();
-  const cd* res = chunk_forward(a, r0, cnt, buf0, buf1, scratch);
+  if (threadIdx.x >= NCW * 32) {
+    if (threadIdx.x == NCW * 32) {
+      Producer pr;
+      ring_produce<true>(a, rg, rg, pr, r0, cnt);
+    }
+    return;
+  }
+  for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = a.fin[static_cast<size_t>(r0) * SB + e];
+  consumer_sync();
+  RingPos pos{0, 0u};
+  const cd* res = chunk_forward(a, rg, pos, r0, cnt, buf0, buf1, part);
   if (threadIdx.x < SB) a.fout[static_cast<size_t>(blockIdx.x) * SB + threadIdx.x] = res[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(256, 3) slu_bwd_stage_kernel(StageArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// smem: [ns slots][nu U slots][z (C + 1) x 32][part][barriers]
+__global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArgs a, int ns, int nu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = 1 << a.mu;
-  cd* z = reinterpret_cast<cd*>(smem_raw);   // (C + 1) x 32
-  cd* ustage = z + (C + 1) * SB;             // 4 groups x TRI
-  cd* scratch = ustage + 4 * TRI;            // 8 warps x 64
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
+  cd* uslots = sc.take<cd>(static_cast<size_t>(nu) * TRI);
+  cd* z = sc.take<cd>((C + 1) * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);
+  uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
+  const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
+  if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
+  __syncthreads();
   const int r0 = blockIdx.x * C;
   const int cnt = min(C, a.m0 - r0);
-  prefetch_records(a, r0, cnt, 0, PR_E, PR_U + TRI);
+  if (threadIdx.x >= NCW * 32) {
+    if (threadIdx.x == NCW * 32) {
+      Producer pr;
+      ring_produce<false>(a, rg, ur, pr, r0, cnt);
+    }
+    return;
+  }
   if (threadIdx.x < SB) z[threadIdx.x] = a.xv[unknown_index(a, r0) * SB + threadIdx.x];
   else if (threadIdx.x < 2 * SB)
     z[cnt * SB + threadIdx.x - SB] = a.xv[unknown_index(a, r0 + cnt) * SB + threadIdx.x - SB];
-  __syncthreads();
-  chunk_backward(a, r0, cnt, z, ustage, scratch);
+  consumer_sync();
+  RingPos pos{0, 0u}, upos{0, 0u};
+  chunk_backward(a, rg, pos, ur, upos, r0, cnt, z, part);
 }
 
 // Single CTA: remaining levels forward, dense top system, back substitution.
-__global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// smem: [ns slots][nu U slots][buf0][buf1][z][part][big 64 x 64 + 64][barriers]
+__global__ void __launch_bounds__(RING_THREADS) slu_top_stage_kernel(StageArgs a, int ns, int nu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int C = 1 << a.mu;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  cd* buf0 = reinterpret_cast<cd*>(smem_raw);
-  cd* buf1 = buf0 + C * SB;
-  cd* z = buf1 + C * SB;                  // (C + 1) x 32
-  cd* scratch = z + (C + 1) * SB;         // 8 x 64
-  cd* big = scratch + 8 * 2 * SB;         // max(8 * TRI, 64 * 64 + 64): top U / U stages
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
+  cd* uslots = sc.take<cd>(static_cast<size_t>(nu) * TRI);
+  cd* buf0 = sc.take<cd>(C * SB);
+  cd* buf1 = sc.take<cd>(C * SB);
+  cd* z = sc.take<cd>((C + 1) * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);     // doubles as the 8 x 64 scratch of the dense step
+  cd* big = sc.take<cd>(64 * 64 + 64);      // staged top U, then the 64 right-hand-side entries
+  uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
+  const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
   const int cnt = a.m0;
   const int TS = a.top_size;
-  // everything this CTA will read is static: pull it into L2 up front
-  prefetch_records(a, 0, cnt, 1, PR_PERM, PR_FWD_END);
-  prefetch_records(a, 0, cnt, 0, PR_E, PR_U + TRI);
-  for (int e = tid; e < TOP_STRIDE / 8; e += blockDim.x)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.top + e * 8));
-  for (int e = tid; e < cnt * SB; e += blockDim.x) buf0[e] = a.fin[e];
+  if (tid == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
   __syncthreads();
+  if (tid >= NCW * 32) {
+    if (tid == NCW * 32 && cnt > 0) {
+      Producer pr;
+      ring_produce<true>(a, rg, ur, pr, 0, cnt);
+      ring_produce<false>(a, rg, ur, pr, 0, cnt);
+    }
+    return;
+  }
+  for (int e = tid; e < 64 * 64; e += NCW * 32) cp_async16(big + e, a.top + TOP_U + e);
+  cp_async_commit();
+  for (int e = tid; e < cnt * SB; e += NCW * 32) buf0[e] = a.fin[e];
+  consumer_sync();
+  RingPos pos{0, 0u}, upos{0, 0u};
   const cd* res = buf0;
-  if (cnt > 0) res = chunk_forward(a, 0, cnt, buf0, buf1, scratch);
+  if (cnt > 0) res = chunk_forward(a, rg, pos, 0, cnt, buf0, buf1, part);
   // ---- top system: [boundary row of node 0 ; last reduced row ; boundary row of node n_pad-1]
-  cd* t = big + 64 * 64;   // 64 entries behind the staged U
+  cd* t = big + 64 * 64;
   if (tid < 64) {
     cd v{0.0, 0.0};
     if (tid < 16) v = a.b[tid];
@@ -380,9 +491,7 @@ __global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
     }
     t[tid] = v;
   }
-  for (int e = tid; e < 64 * 64; e += blockDim.x) cp_async16(big + e, a.top + TOP_U + e);
-  cp_async_commit();
-  __syncthreads();
+  consumer_sync();
   // y = Linv (P t): 8 warps x 8 columns each, two rows per lane
   {
     const uint8_t* perm = reinterpret_cast<const uint8_t*>(a.top);
@@ -399,27 +508,27 @@ __global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
       cfma(p0, m0[c], tv);
       cfma(p1, m1[c], tv);
     }
-    scratch[warp * 64 + lane] = p0;
-    scratch[warp * 64 + 32 + lane] = p1;
+    part[warp * 64 + lane] = p0;
+    part[warp * 64 + 32 + lane] = p1;
   }
   cp_async_wait_all();
-  __syncthreads();
+  consumer_sync();
   if (warp == 0) {
     cd y0{0.0, 0.0}, y1{0.0, 0.0};   // rows lane and lane + 32
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { y0 += scratch[w * 64 + lane]; y1 += scratch[w * 64 + 32 + lane]; }
-    // back substitution with U (column-major, ld 64, reciprocal diagonal), one warp
-    for (int k = TS - 1; k >= 0; --k) {
+    for (int w = 0; w < 8; ++w) { y0 += part[w * 64 + lane]; y1 += part[w * 64 + 32 + lane]; }
+    // unit upper triangular back substitution (rows pre-divided by their diagonal, whose
+    // reciprocal sits on the diagonal), column-major with leading dimension 64
+    y0 = y0 * big[lane * 64 + lane];
+    y1 = y1 * big[(lane + 32) * 64 + lane + 32];
+    for (int k = TS - 1; k >= 1; --k) {
       const cd* col = big + k * 64;
-      const cd cand = (k >= 32 ? y1 : y0) * col[k];
-      const cd xk = shfl_cd(cand, k & 31);
+      const cd xk = shfl_cd(k >= 32 ? y1 : y0, k & 31);
       if (k >= 32) {
         if (lane + 32 < k) cfms(y1, col[lane + 32], xk);
-        else if (lane + 32 == k) y1 = xk;
         cfms(y0, col[lane], xk);
-      } else {
-        if (lane < k) cfms(y0, col[lane], xk);
-        else if (lane == k) y0 = xk;
+      } else if (lane < k) {
+        cfms(y0, col[lane], xk);
       }
     }
     z[lane] = y0;
@@ -429,8 +538,8 @@ __global__ void __launch_bounds__(256) slu_top_stage_kernel(StageArgs a) {
       a.xv[static_cast<size_t>(a.K - 1) * SB + lane] = y1;
     }
   }
-  __syncthreads();
-  if (cnt > 0) chunk_backward(a, 0, cnt, z, big, scratch);
+  consumer_sync();
+  if (cnt > 0) chunk_backward(a, rg, pos, ur, upos, 0, cnt, z, part);
 }
 
 // ------------------------------------------------------------------ factorisation kernels
@@ -486,7 +595,7 @@ constexpr int WLD = 97;   // padded row length of the 64 x 96 working matrix
 // Merge rows (2p, 2p+1) of a level: GE with partial pivoting over the 64 stacked rows of the
 // panel [T_2p ; S_2p+1]; block npairs (if present) carries the odd last row up unchanged.
 __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* W = reinterpret_cast<cd*>(smem_raw);          // [64][WLD]
   cd* X = W + 64 * WLD;                             // [32][33] inverse of L11
   cd* lcol = X + SB * 33;                           // [64]
@@ -599,7 +708,11 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     rec[PR_L21 + e] = W[(32 + i) * WLD + c] * (1.0 / rscale[prm[32 + i]]);
     rec[PR_E + e] = W[i * WLD + 32 + c];
     rec[PR_F + e] = W[i * WLD + 64 + c];
-    if (i <= c) rec[PR_U + tri_up_off(c) + i] = (i == c) ? crecip(W[i * WLD + c]) : W[i * WLD + c];
+    // U leaves with unit diagonal: row i divided by U_ii, whose reciprocal takes the diagonal slot
+    if (i <= c) {
+      const cd dinv = crecip(W[i * WLD + i]);
+      rec[PR_U + tri_up_off(c) + i] = (i == c) ? dinv : W[i * WLD + c] * dinv;
+    }
   }
   cd* Sn = a.dst + static_cast<size_t>(p) * ROW_STRIDE;
   cd* Tn = Sn + SB2;
@@ -615,7 +728,7 @@ constexpr int TLD = 65;
 
 // Dense top system: rows [node 0 ; last reduced row ; node n_pad - 1] on (z_0, z_K-1).
 __global__ void __launch_bounds__(256) slu_top_factor_kernel(FactorArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* W = reinterpret_cast<cd*>(smem_raw);       // [64][TLD]
   cd* X = W + 64 * TLD;                          // [64][TLD] inverse of L
   cd* lcol = X + 64 * TLD;
@@ -716,7 +829,7 @@ __global__ void __launch_bounds__(256) slu_top_factor_kernel(FactorArgs a) {
     const int i = e & 63, c = e >> 6;   // column-major, leading dimension 64
     a.top[TOP_LINV + e] = X[i * TLD + c] * rscale[prm[c]];
     cd u{0.0, 0.0};
-    if (i < c) u = W[i * TLD + c];
+    if (i < c && c < TS) u = W[i * TLD + c] * crecip(W[i * TLD + i]);
     else if (i == c) u = crecip(W[i * TLD + c]);
     a.top[TOP_U + e] = u;
   }
@@ -789,18 +902,53 @@ StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const 
   return a;
 }
 
-size_t fwd_smem(int mu) { return sizeof(cd) * ((2 << mu) * SB + 8 * 2 * SB); }
-size_t bwd_smem(int mu) { return sizeof(cd) * (((1 << mu) + 1) * SB + 4 * TRI + 8 * 2 * SB); }
-size_t top_smem(int mu) {
-  return sizeof(cd) * ((2 << mu) * SB + ((1 << mu) + 1) * SB + 8 * 2 * SB + 64 * 64 + 64 + 8 * TRI);
+// ---- shared-memory budgets of the solve kernels
+// Three CTAs per SM (232448 B of shared memory, 1 KB reserved per CTA) keep every chunk of the
+// first stage resident at once; the narrow upper stages get the whole SM.
+constexpr size_t SMEM_PER_CTA_3 = (232448 - 3 * 1024) / 3;
+constexpr size_t SMEM_PER_CTA_1 = 232448 - 1024;
+
+struct RingShape {
+  int ns, nu;
+  size_t bytes;
+};
+size_t fwd_smem(int mu, int ns) {
+  return sizeof(cd) * (static_cast<size_t>(ns) * GRAN + (2 << mu) * SB + 2 * NCW * SB) + 16 * ns;
 }
+size_t bwd_smem(int mu, int ns, int nu) {
+  return sizeof(cd) * (static_cast<size_t>(ns) * GRAN + static_cast<size_t>(nu) * TRI +
+                       ((1 << mu) + 1) * SB + 2 * NCW * SB) + 16 * (ns + nu);
+}
+size_t top_smem(int mu, int ns, int nu) {
+  return sizeof(cd) * (static_cast<size_t>(ns) * GRAN + static_cast<size_t>(nu) * TRI + (2 << mu) * SB +
+                       ((1 << mu) + 1) * SB + 2 * NCW * SB + 64 * 64 + 64) + 16 * (ns + nu);
+}
+RingShape fwd_shape(const StageArgs& a) {
+  const size_t budget = a.nchunks > 148 ? SMEM_PER_CTA_3 : SMEM_PER_CTA_1;
+  int ns = 2;
+  while (ns < 8 && fwd_smem(a.mu, ns + 1) <= budget) ++ns;
+  return RingShape{ns, 0, fwd_smem(a.mu, ns)};
+}
+// U slots first (parallel solves per level, ideally twice the widest level so that the next
+// batch loads during the current solves), then block slots with what is left
+RingShape bwd_shape(const StageArgs& a, bool top) {
+  const size_t budget = (!top && a.nchunks > 148) ? SMEM_PER_CTA_3 : SMEM_PER_CTA_1;
+  auto bytes = [&](int ns, int nu) { return top ? top_smem(a.mu, ns, nu) : bwd_smem(a.mu, ns, nu); };
+  const int widest = std::max(1, (1 << a.mu) / 2);
+  const int nu_max = std::min(16, 2 * std::min(widest, NCW));
+  int ns = 2, nu = 1;
+  while (nu < nu_max && bytes(ns, nu + 1) <= budget) ++nu;
+  while (ns < 6 && bytes(ns + 1, nu) <= budget) ++ns;
+  return RingShape{ns, nu, bytes(ns, nu)};
+}
+
 constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + SB * 33 + 64) + sizeof(int) * 64;
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
   static bool done = false;
   if (done) return;
-  const int big = 200 * 1024;
+  const int big = static_cast<int>(SMEM_PER_CTA_1);
   CUDA_CHECK(cudaFuncSetAttribute(slu_fwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_bwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -866,19 +1014,22 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
   for (int s = 0; s < ns - 1; ++s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv);
     log->begin(s == 0 ? LK_FWD0 : LK_FWD, stage_algo_bytes(plan, s, 7936.0));
-    slu_fwd_stage_kernel<<<a.nchunks, 256, fwd_smem(a.mu), stream>>>(a);
+    const RingShape sh = fwd_shape(a);
+    slu_fwd_stage_kernel<<<a.nchunks, RING_THREADS, sh.bytes, stream>>>(a, sh.ns);
     log->end();
   }
   {
     const StageArgs a = make_stage_args(plan, d, ns - 1, b, xv);
     log->begin(LK_TOP, stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2);
-    slu_top_stage_kernel<<<1, 256, top_smem(a.mu), stream>>>(a);
+    const RingShape sh = bwd_shape(a, true);
+    slu_top_stage_kernel<<<1, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
     log->end();
   }
   for (int s = ns - 2; s >= 0; --s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv);
     log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
-    slu_bwd_stage_kernel<<<a.nchunks, 256, bwd_smem(a.mu), stream>>>(a);
+    const RingShape sh = bwd_shape(a, false);
+    slu_bwd_stage_kernel<<<a.nchunks, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
     log->end();
   }
   log->launches += 2 * (ns - 1) + 1;
