@@ -87,6 +87,8 @@ struct lgpu_ctx {
   SluPlan splan;
   DevBuf<cd> pairs, topfac, fwork, rhs, gvec, xpad;
   DevBuf<int32_t> d_info;
+  DevBuf<unsigned long long> d_sync;
+  unsigned long long solve_epoch = 0;
   bool factorized = false;
   cd sigma{0.0, 0.0};
   int lu_info = 0;
@@ -109,6 +111,7 @@ struct lgpu_ctx {
     SluDevice d{};
     d.A = A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
     d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
+    d.sync = d_sync.p; d.epoch = &solve_epoch;
     return d;
   }
 };
@@ -250,6 +253,7 @@ int do_factorize(lgpu_ctx* c, cd sigma) {
     c->gvec.ensure(std::max<size_t>(c->splan.pair_records, 1) * SB);
     c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
     c->d_info.ensure(1);
+    c->d_sync.ensure(SLU_SYNC_COUNTERS);
     // Keep the factor records of the narrow upper levels (latency-bound, ~20 MB at G = 10001)
     // resident in L2: persisting access-policy window on the context's stream.
     const int nl = static_cast<int>(c->splan.levels.size());
@@ -274,6 +278,9 @@ int do_factorize(lgpu_ctx* c, cd sigma) {
   }
   ensure_vectors(c);
   c->log.stream = c->stream;
+  // the fused solve stages count finished chunks cumulatively from here on
+  CUDA_CHECK(cudaMemsetAsync(c->d_sync.p, 0, sizeof(unsigned long long) * SLU_SYNC_COUNTERS, c->stream));
+  c->solve_epoch = 0;
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
   slu_factorize(c->splan, c->sdev(), sigma, c->stream, &c->log);
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));

@@ -8,6 +8,9 @@ namespace lgpu {
 
 // ============================================================================= plan
 SluPlan make_slu_plan(int n, int first_stage_mu, int next_stage_mu, int top_max_rows) {
+  first_stage_mu = std::max(1, std::min(first_stage_mu, 6));
+  next_stage_mu = std::max(1, std::min(next_stage_mu, 6));
+  top_max_rows = std::max(2, std::min(top_max_rows, 64));
   SluPlan p;
   p.n = n;
   p.n_pad = n + (n & 1);
@@ -79,6 +82,7 @@ __device__ __forceinline__ int tri_lo_off(int c) { return c * SB - (c * (c - 1))
 __device__ __forceinline__ int tri_up_off(int k) { return (k * (k + 1)) / 2; }
 
 constexpr int MAX_STAGE_LEVELS = 14;
+constexpr int MAX_FUSED = 6;          // stages one cooperative launch can chain (incl. the top stage)
 
 struct LevelRef {
   int m;
@@ -383,100 +387,51 @@ struct SmemCursor {
   }
 };
 
-// smem: [ns slots][buf0 C x 32][buf1 C x 32][part 2 x NCW x 32][2 ns barriers]
-__global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArgs a, int ns) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int C = 1 << a.mu;
-  SmemCursor sc{smem_raw};
-  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
-  cd* buf0 = sc.take<cd>(C * SB);
-  cd* buf1 = sc.take<cd>(C * SB);
-  cd* part = sc.take<cd>(2 * NCW * SB);
-  uint64_t* bars = sc.take<uint64_t>(2 * ns);
-  const Ring rg{slots, bars, bars + ns, ns, GRAN};
-  if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init_fence(); }
-  __syncthreads();
-  const int r0 = blockIdx.x * C;
-  const int cnt = min(C, a.m0 - r0);
-  if (threadIdx.x >= NCW * 32) {
-    if (threadIdx.x == NCW * 32) {
-      Producer pr;
-      ring_produce<true>(a, rg, rg, pr, r0, cnt);
-    }
-    return;
-  }
-  for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = a.fin[static_cast<size_t>(r0) * SB + e];
-  consumer_sync();
-  RingPos pos{0, 0u};
-  const cd* res = chunk_forward(a, rg, pos, r0, cnt, buf0, buf1, part);
-  if (threadIdx.x < SB) a.fout[static_cast<size_t>(blockIdx.x) * SB + threadIdx.x] = res[threadIdx.x];
+// ---- stage bodies (consumer warps only) --------------------------------------------------
+// Right-hand sides and boundary unknowns may have been written by another CTA of the same
+// launch (fused upper stages): they are read past L1 (ld.global.cg).
+__device__ __forceinline__ cd ldcg_cd(const cd* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return cd{v.x, v.y};
 }
 
-// smem: [ns slots][nu U slots][z (C + 1) x 32][part][barriers]
-__global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArgs a, int ns, int nu) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__device__ __forceinline__ void fwd_stage_body(const StageArgs& a, int chunk, const Ring& rg, RingPos& pos,
+                                               cd* buf0, cd* buf1, cd* part) {
   const int C = 1 << a.mu;
-  SmemCursor sc{smem_raw};
-  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
-  cd* uslots = sc.take<cd>(static_cast<size_t>(nu) * TRI);
-  cd* z = sc.take<cd>((C + 1) * SB);
-  cd* part = sc.take<cd>(2 * NCW * SB);
-  uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
-  const Ring rg{slots, bars, bars + ns, ns, GRAN};
-  const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
-  if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
-  __syncthreads();
-  const int r0 = blockIdx.x * C;
+  const int r0 = chunk * C;
   const int cnt = min(C, a.m0 - r0);
-  if (threadIdx.x >= NCW * 32) {
-    if (threadIdx.x == NCW * 32) {
-      Producer pr;
-      ring_produce<false>(a, rg, ur, pr, r0, cnt);
-    }
-    return;
-  }
-  if (threadIdx.x < SB) z[threadIdx.x] = a.xv[unknown_index(a, r0) * SB + threadIdx.x];
-  else if (threadIdx.x < 2 * SB)
-    z[cnt * SB + threadIdx.x - SB] = a.xv[unknown_index(a, r0 + cnt) * SB + threadIdx.x - SB];
+  for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + static_cast<size_t>(r0) * SB + e);
   consumer_sync();
-  RingPos pos{0, 0u}, upos{0, 0u};
+  const cd* res = chunk_forward(a, rg, pos, r0, cnt, buf0, buf1, part);
+  if (threadIdx.x < SB) a.fout[static_cast<size_t>(chunk) * SB + threadIdx.x] = res[threadIdx.x];
+}
+
+__device__ __forceinline__ void bwd_stage_body(const StageArgs& a, int chunk, const Ring& rg, RingPos& pos,
+                                               const Ring& ur, RingPos& upos, cd* z, cd* part) {
+  const int C = 1 << a.mu;
+  const int r0 = chunk * C;
+  const int cnt = min(C, a.m0 - r0);
+  if (threadIdx.x < SB) z[threadIdx.x] = ldcg_cd(a.xv + unknown_index(a, r0) * SB + threadIdx.x);
+  else if (threadIdx.x < 2 * SB)
+    z[cnt * SB + threadIdx.x - SB] = ldcg_cd(a.xv + unknown_index(a, r0 + cnt) * SB + threadIdx.x - SB);
+  consumer_sync();
   chunk_backward(a, rg, pos, ur, upos, r0, cnt, z, part);
 }
 
-// Single CTA: remaining levels forward, dense top system, back substitution.
-// smem: [ns slots][nu U slots][buf0][buf1][z][part][big 64 x 64 + 64][barriers]
-__global__ void __launch_bounds__(RING_THREADS) slu_top_stage_kernel(StageArgs a, int ns, int nu) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int C = 1 << a.mu;
+// stage the dense top U (64 x 64) into shared memory; waited for inside top_stage_body
+__device__ __forceinline__ void top_stage_prefetch(const StageArgs& a, cd* big) {
+  for (int e = threadIdx.x; e < 64 * 64; e += NCW * 32) cp_async16(big + e, a.top + TOP_U + e);
+  cp_async_commit();
+}
+
+// remaining levels forward, dense top system, back substitution (one CTA)
+__device__ __forceinline__ void top_stage_body(const StageArgs& a, const Ring& rg, RingPos& pos, const Ring& ur,
+                                               RingPos& upos, cd* buf0, cd* buf1, cd* z, cd* part, cd* big) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  SmemCursor sc{smem_raw};
-  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
-  cd* uslots = sc.take<cd>(static_cast<size_t>(nu) * TRI);
-  cd* buf0 = sc.take<cd>(C * SB);
-  cd* buf1 = sc.take<cd>(C * SB);
-  cd* z = sc.take<cd>((C + 1) * SB);
-  cd* part = sc.take<cd>(2 * NCW * SB);     // doubles as the 8 x 64 scratch of the dense step
-  cd* big = sc.take<cd>(64 * 64 + 64);      // staged top U, then the 64 right-hand-side entries
-  uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
-  const Ring rg{slots, bars, bars + ns, ns, GRAN};
-  const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
   const int cnt = a.m0;
   const int TS = a.top_size;
-  if (tid == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
-  __syncthreads();
-  if (tid >= NCW * 32) {
-    if (tid == NCW * 32 && cnt > 0) {
-      Producer pr;
-      ring_produce<true>(a, rg, ur, pr, 0, cnt);
-      ring_produce<false>(a, rg, ur, pr, 0, cnt);
-    }
-    return;
-  }
-  for (int e = tid; e < 64 * 64; e += NCW * 32) cp_async16(big + e, a.top + TOP_U + e);
-  cp_async_commit();
-  for (int e = tid; e < cnt * SB; e += NCW * 32) buf0[e] = a.fin[e];
+  for (int e = tid; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + e);
   consumer_sync();
-  RingPos pos{0, 0u}, upos{0, 0u};
   const cd* res = buf0;
   if (cnt > 0) res = chunk_forward(a, rg, pos, 0, cnt, buf0, buf1, part);
   // ---- top system: [boundary row of node 0 ; last reduced row ; boundary row of node n_pad-1]
@@ -540,6 +495,181 @@ __global__ void __launch_bounds__(RING_THREADS) slu_top_stage_kernel(StageArgs a
   }
   consumer_sync();
   if (cnt > 0) chunk_backward(a, rg, pos, ur, upos, 0, cnt, z, part);
+}
+
+// smem: [ns slots][buf0 C x 32][buf1 C x 32][part 2 x NCW x 32][2 ns barriers]
+__global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArgs a, int ns) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = 1 << a.mu;
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
+  cd* buf0 = sc.take<cd>(C * SB);
+  cd* buf1 = sc.take<cd>(C * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);
+  uint64_t* bars = sc.take<uint64_t>(2 * ns);
+  const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init_fence(); }
+  __syncthreads();
+  if (threadIdx.x >= NCW * 32) {
+    if (threadIdx.x == NCW * 32) {
+      Producer pr;
+      const int r0 = blockIdx.x * C;
+      ring_produce<true>(a, rg, rg, pr, r0, min(C, a.m0 - r0));
+    }
+    return;
+  }
+  RingPos pos{0, 0u};
+  fwd_stage_body(a, blockIdx.x, rg, pos, buf0, buf1, part);
+}
+
+// smem: [ns slots][nu U slots][z (C + 1) x 32][part][barriers]
+__global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArgs a, int ns, int nu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = 1 << a.mu;
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
+  cd* uslots = sc.take<cd>(static_cast<size_t>(nu) * TRI);
+  cd* z = sc.take<cd>((C + 1) * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);
+  uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
+  const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
+  if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
+  __syncthreads();
+  if (threadIdx.x >= NCW * 32) {
+    if (threadIdx.x == NCW * 32) {
+      Producer pr;
+      const int r0 = blockIdx.x * C;
+      ring_produce<false>(a, rg, ur, pr, r0, min(C, a.m0 - r0));
+    }
+    return;
+  }
+  RingPos pos{0, 0u}, upos{0, 0u};
+  bwd_stage_body(a, blockIdx.x, rg, pos, ur, upos, z, part);
+}
+
+// The narrow upper stages and the top system in ONE cooperative launch (grid = chunks of the first
+// fused stage, all co-resident): their data is a few MB, their cost is the dependency chain,
+// and a kernel boundary per stage (launch gap, ring start-up) would double it.  CTAs meet through
+// monotonic device counters: stage s forward done (sync[s]) and backward done
+// (sync[MAX_FUSED + s]) count finished chunks over all solves since the factorisation; solve
+// number `epoch` waits for epoch * chunks.  The producer warp never waits on them (the factor
+// records are static), so the next stage's records are on chip when its dependencies arrive.
+struct FusedArgs {
+  int nst;                       // fused stages; the last one is the top stage
+  int ns, nu, cmax;              // ring shapes, rows of the widest chunk
+  unsigned long long epoch;      // 1, 2, ... since the counters were cleared
+  unsigned long long* sync;      // 2 * MAX_FUSED counters
+  StageArgs st[MAX_FUSED];
+};
+
+__device__ __forceinline__ void grid_signal(unsigned long long* ctr) {
+  __threadfence();
+  consumer_sync();
+  if (threadIdx.x == 0) atomicAdd(ctr, 1ULL);
+}
+__device__ __forceinline__ void grid_wait(const unsigned long long* ctr, unsigned long long target) {
+  if (threadIdx.x == 0) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  consumer_sync();
+  __threadfence();
+}
+
+// smem: [ns slots][nu U slots][buf0][buf1][z][part][big 64 x 64 + 64][barriers], sized for cmax
+__global__ void __launch_bounds__(RING_THREADS) slu_fused_stage_kernel(const __grid_constant__ FusedArgs f) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(f.ns) * GRAN);
+  cd* uslots = sc.take<cd>(static_cast<size_t>(f.nu) * TRI);
+  cd* buf0 = sc.take<cd>(f.cmax * SB);
+  cd* buf1 = sc.take<cd>(f.cmax * SB);
+  cd* z = sc.take<cd>((f.cmax + 1) * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);
+  cd* big = sc.take<cd>(64 * 64 + 64);
+  uint64_t* bars = sc.take<uint64_t>(2 * (f.ns + f.nu));
+  const Ring rg{slots, bars, bars + f.ns, f.ns, GRAN};
+  const Ring ur{uslots, bars + 2 * f.ns, bars + 2 * f.ns + f.nu, f.nu, TRI};
+  if (tid == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
+  __syncthreads();
+  const int top = f.nst - 1;
+  if (tid >= NCW * 32) {
+    if (tid == NCW * 32) {
+      Producer pr;
+      for (int s = 0; s < top; ++s) {
+        const StageArgs& a = f.st[s];
+        const int C = 1 << a.mu;
+        if (b < a.nchunks) ring_produce<true>(a, rg, ur, pr, b * C, min(C, a.m0 - b * C));
+      }
+      if (b == 0 && f.st[top].m0 > 0) {
+        ring_produce<true>(f.st[top], rg, ur, pr, 0, f.st[top].m0);
+        ring_produce<false>(f.st[top], rg, ur, pr, 0, f.st[top].m0);
+      }
+      for (int s = top - 1; s >= 0; --s) {
+        const StageArgs& a = f.st[s];
+        const int C = 1 << a.mu;
+        if (b < a.nchunks) ring_produce<false>(a, rg, ur, pr, b * C, min(C, a.m0 - b * C));
+      }
+    }
+    return;
+  }
+  if (b == 0) top_stage_prefetch(f.st[top], big);
+  RingPos pos{0, 0u}, upos{0, 0u};
+  for (int s = 0; s < top; ++s) {
+    const StageArgs& a = f.st[s];
+    if (b >= a.nchunks) continue;
+    if (s > 0) grid_wait(f.sync + s - 1, f.epoch * f.st[s - 1].nchunks);
+    fwd_stage_body(a, b, rg, pos, buf0, buf1, part);
+    grid_signal(f.sync + s);
+  }
+  if (b == 0) {
+    if (top > 0) grid_wait(f.sync + top - 1, f.epoch * f.st[top - 1].nchunks);
+    top_stage_body(f.st[top], rg, pos, ur, upos, buf0, buf1, z, part, big);
+    grid_signal(f.sync + MAX_FUSED + top);
+  }
+  for (int s = top - 1; s >= 0; --s) {
+    const StageArgs& a = f.st[s];
+    if (b >= a.nchunks) continue;
+    grid_wait(f.sync + MAX_FUSED + s + 1, f.epoch * (s + 1 == top ? 1 : f.st[s + 1].nchunks));
+    bwd_stage_body(a, b, rg, pos, ur, upos, z, part);
+    grid_signal(f.sync + MAX_FUSED + s);
+  }
+}
+
+// Single CTA: the top stage alone (problems too small for more than one stage above the first).
+// smem: [ns slots][nu U slots][buf0][buf1][z][part][big 64 x 64 + 64][barriers]
+__global__ void __launch_bounds__(RING_THREADS) slu_top_stage_kernel(StageArgs a, int ns, int nu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int C = 1 << a.mu;
+  const int tid = threadIdx.x;
+  SmemCursor sc{smem_raw};
+  cd* slots = sc.take<cd>(static_cast<size_t>(ns) * GRAN);
+  cd* uslots = sc.take<cd>(static_cast<size_t>(nu) * TRI);
+  cd* buf0 = sc.take<cd>(C * SB);
+  cd* buf1 = sc.take<cd>(C * SB);
+  cd* z = sc.take<cd>((C + 1) * SB);
+  cd* part = sc.take<cd>(2 * NCW * SB);     // doubles as the 8 x 64 scratch of the dense step
+  cd* big = sc.take<cd>(64 * 64 + 64);      // staged top U, then the 64 right-hand-side entries
+  uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
+  const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
+  if (tid == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
+  __syncthreads();
+  if (tid >= NCW * 32) {
+    if (tid == NCW * 32 && a.m0 > 0) {
+      Producer pr;
+      ring_produce<true>(a, rg, ur, pr, 0, a.m0);
+      ring_produce<false>(a, rg, ur, pr, 0, a.m0);
+    }
+    return;
+  }
+  top_stage_prefetch(a, big);
+  RingPos pos{0, 0u}, upos{0, 0u};
+  top_stage_body(a, rg, pos, ur, upos, buf0, buf1, z, part, big);
 }
 
 // ------------------------------------------------------------------ factorisation kernels
@@ -952,6 +1082,7 @@ void configure_kernels() {
   CUDA_CHECK(cudaFuncSetAttribute(slu_fwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_bwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_fused_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   done = true;
@@ -1006,33 +1137,74 @@ static double stage_algo_bytes(const SluPlan& plan, int s, double per_point) {
   return pairs * 2.0 * per_point + 512.0 * (st.m0 + st.nchunks);
 }
 
+// first stage (>= 1) from which the rest of the solve runs as one cooperative launch, or the
+// index of the top stage when there is nothing to fuse
+static int first_fused_stage(const SluPlan& plan) {
+  static const int sm_count = [] {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  static const bool enabled = [] { const char* e = std::getenv("LGPU_SLU_FUSE"); return !(e && e[0] == '0'); }();
+  const int ns = static_cast<int>(plan.stages.size());
+  if (!enabled || ns < 3) return ns - 1;
+  int sf = std::max(1, ns - MAX_FUSED);
+  while (sf < ns - 1 && plan.stages[sf].nchunks > sm_count) ++sf;   // one CTA per SM, all resident
+  return sf;
+}
+
 void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
                LaunchLog* log) {
   configure_kernels();
   const int ns = static_cast<int>(plan.stages.size());
+  const int sf = first_fused_stage(plan);
   cd* xv = plan.n_pad == plan.n ? x : d.xpad;
-  for (int s = 0; s < ns - 1; ++s) {
+  for (int s = 0; s < sf; ++s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv);
     log->begin(s == 0 ? LK_FWD0 : LK_FWD, stage_algo_bytes(plan, s, 7936.0));
     const RingShape sh = fwd_shape(a);
     slu_fwd_stage_kernel<<<a.nchunks, RING_THREADS, sh.bytes, stream>>>(a, sh.ns);
     log->end();
   }
-  {
+  double top_bytes = stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2;
+  if (sf == ns - 1) {
     const StageArgs a = make_stage_args(plan, d, ns - 1, b, xv);
-    log->begin(LK_TOP, stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2);
+    log->begin(LK_TOP, top_bytes);
     const RingShape sh = bwd_shape(a, true);
     slu_top_stage_kernel<<<1, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
     log->end();
+  } else {
+    FusedArgs f{};
+    f.nst = ns - sf;
+    f.cmax = 1;
+    int mu_max = 0;
+    for (int s = sf; s < ns; ++s) {
+      f.st[s - sf] = make_stage_args(plan, d, s, b, xv);
+      mu_max = std::max(mu_max, plan.stages[s].mu);
+      if (s < ns - 1) top_bytes += stage_algo_bytes(plan, s, 24064.0);
+    }
+    f.cmax = 1 << mu_max;
+    StageArgs widest = f.st[0];
+    widest.mu = mu_max;
+    const RingShape sh = bwd_shape(widest, true);
+    f.ns = sh.ns; f.nu = sh.nu;
+    f.sync = d.sync;
+    f.epoch = ++*d.epoch;
+    void* args[] = {&f};
+    log->begin(LK_TOP, top_bytes);
+    CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(slu_fused_stage_kernel), dim3(f.st[0].nchunks),
+                                           dim3(RING_THREADS), args, sh.bytes, stream));
+    log->end();
   }
-  for (int s = ns - 2; s >= 0; --s) {
+  for (int s = sf - 1; s >= 0; --s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv);
     log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
     const RingShape sh = bwd_shape(a, false);
     slu_bwd_stage_kernel<<<a.nchunks, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
     log->end();
   }
-  log->launches += 2 * (ns - 1) + 1;
+  log->launches += 2 * sf + 1;
   if (xv != x) {
     CUDA_CHECK(cudaMemcpyAsync(x, xv, sizeof(cd) * plan.n * BLK, cudaMemcpyDeviceToDevice, stream));
   }

@@ -99,7 +99,10 @@ struct SluDevice {
   cd* gvec;             // plan.pair_records * 32  (pivot-row right-hand sides of the last solve)
   cd* xpad;             // n_pad * 16 solution scratch when n is odd
   int32_t* info;        // singular-pivot report (1-based block row, 0 = none)
+  unsigned long long* sync;    // SLU_SYNC_COUNTERS device counters of the fused upper stages
+  unsigned long long* epoch;   // host: solves since the counters were last cleared
 };
+constexpr int SLU_SYNC_COUNTERS = 16;
 
 void slu_factorize(const SluPlan& plan, const SluDevice& d, cd sigma, cudaStream_t stream,
                    LaunchLog* log);
