@@ -340,8 +340,7 @@ class CudaKrylovOps final : public KrylovOps {
       dev_apply_op(c_, c_->vcur.p, c_->resid.p, refine_);
       cd* hcol = H + static_cast<size_t>(j) * ncv_;
       krylov_dots(L, V, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->log);
-      krylov_update(L, V, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
-      krylov_dots(L, V, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
+      krylov_update_dots(L, V, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
       krylov_update(L, V, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
     }
   }

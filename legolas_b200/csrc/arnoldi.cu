@@ -1,10 +1,11 @@
 // K3b / K3c — see arnoldi.cuh.
 //
-// All kernels here are pure streaming kernels over the N x ncv basis (HBM-bound): every
-// global access is a 16-byte complex load/store with consecutive lanes on consecutive rows
-// (the basis is column-major, like ARPACK's V), reductions are two-level (CTA partials, then
-// the last CTA to finish sums the partials in a fixed order), so results are deterministic.
+// All kernels here are pure streaming kernels over the N x ncv basis (HBM-bound).  Reductions
+// are two-level (CTA partials, then the last CTA to finish sums the partials in a fixed
+// order), so results are deterministic.
 #include "arnoldi.cuh"
+
+#include <algorithm>
 
 namespace lgpu {
 namespace {
@@ -37,134 +38,169 @@ __device__ __forceinline__ bool last_block_done(unsigned int* ticket, bool wrote
   return is_last;
 }
 
-constexpr int DOT_CHUNK = 8;
+// ---- staged Gram-Schmidt pass -----------------------------------------------------------------
+// One kernel for the three passes of a CGS2 step:
+//   <false, true>   h = V^H w                                   (first projection)
+//   <true,  true>   w -= V h_in ; s = V^H w                     (correction + second projection)
+//   <true,  false>  w -= V h_in ; ||w||                         (second correction + norm)
+// A CTA owns a contiguous range of 64-row tiles (one CTA per SM, ranges differ by at most one
+// tile).  The first ncols columns of a tile are one contiguous block of the basis, so a producer
+// warp streams them with ONE cp.async.bulk per tile into a ring of shared-memory stages.  The
+// 256 consumer threads are 64 rows x 4 column groups: a thread pulls its <= 16 entries of the
+// tile into registers once and uses them for both the correction and the projection, so the
+// fused middle pass reads V once; projections accumulate in registers over the whole tile range
+// and are reduced across rows once per CTA.  Two-level fixed-order reductions (deterministic).
+constexpr int PASS_THREADS = 288;   // warps 0-7 consume, warp 8 produces
+constexpr int PASS_GROUPS = 4;      // column groups
+constexpr int PASS_CPG = KRYLOV_PASS_MAXCOL / PASS_GROUPS;   // columns per thread
+constexpr int PASS_T = KRYLOV_TILE;
 
-// Thread mapping of the dot / update kernels: one CTA per tile with T / 2 threads, every
-// thread owns exactly the two rows tid and tid + T/2 of the tile (equal work per thread).
-
-// h = V(:, 0:ncols)^H w.  Columns are processed in chunks of 8: 16 independent 16-byte loads
-// per thread in flight, 8 partial dot products per thread, reduced through shared memory
-// (warp c sums column c).
-__global__ void __launch_bounds__(640)
-krylov_dots_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, const cd* __restrict__ w,
-                   cd* __restrict__ partial, cd* __restrict__ hwork, cd* Hcol, int accumulate,
+template <bool UPDATE, bool DOTS>
+__global__ void __launch_bounds__(PASS_THREADS, 1)
+krylov_pass_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, int nstages, cd* w, const cd* hin,
+                   cd* __restrict__ partial, cd* hwork, cd* Hcol, int accumulate, double* scal,
                    unsigned int* ticket) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cd* red = reinterpret_cast<cd*>(smem_raw);   // [DOT_CHUNK][blockDim.x]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int sstride = (ncols + 1) * PASS_T;                             // stage: [ncols][64] of V, [64] of w
+  cd* buf = reinterpret_cast<cd*>(smem_raw);                            // [nstages][sstride]
+  cd* part = buf + static_cast<size_t>(nstages) * sstride;               // [2][4][64]
+  cd* hs = part + 2 * PASS_GROUPS * PASS_T;                             // [KRYLOV_PASS_MAXCOL]
+  uint64_t* full = reinterpret_cast<uint64_t*>(hs + KRYLOV_PASS_MAXCOL);
+  uint64_t* empty = full + nstages;
+  __shared__ double red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nthr = blockDim.x, nwarps = nthr >> 5;
-  const int row0 = blockIdx.x * L.T;
-  const int rows = min(L.T, L.n - row0);
-  const cd* tile = V + static_cast<size_t>(blockIdx.x) * L.ncv * L.T;
-  const int i0 = tid, i1 = tid + nthr;
-  const bool ok0 = i0 < rows, ok1 = i1 < rows;
-  const cd w0 = ok0 ? w[row0 + i0] : cd{0.0, 0.0}, w1 = ok1 ? w[row0 + i1] : cd{0.0, 0.0};
-  for (int cb = 0; cb < ncols; cb += DOT_CHUNK) {
-    cd a0[DOT_CHUNK], a1[DOT_CHUNK];
+  const int t0 = static_cast<int>(static_cast<long long>(blockIdx.x) * L.ntiles / gridDim.x);
+  const int t1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * L.ntiles / gridDim.x);
+  if (tid == 0) {
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (UPDATE) for (int c = tid; c < ncols; c += PASS_THREADS) hs[c] = hin[c];
+  __syncthreads();
+  const int cpg = (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
+  const int r = tid & (PASS_T - 1), q = (tid >> 6) & 3;
+  cd acc[PASS_CPG];
 #pragma unroll
-    for (int c = 0; c < DOT_CHUNK; ++c) {
-      const bool okc = cb + c < ncols;
-      const cd* col = tile + static_cast<size_t>(cb + c) * L.T;
-      a0[c] = (okc && ok0) ? ldg_cd(col + i0) : cd{0.0, 0.0};
-      a1[c] = (okc && ok1) ? ldg_cd(col + i1) : cd{0.0, 0.0};
+  for (int j = 0; j < PASS_CPG; ++j) acc[j] = cd{0.0, 0.0};
+  double nrm = 0.0;
+  if (warp == 8) {
+    // ---- producer (one lane): tile t -> stage (t - t0) % nstages
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncols * PASS_T);
+      for (int t = t0; t < t1; ++t) {
+        if (t - t0 >= nstages) mbar_wait(&empty[stage], phase ^ 1u);
+        cd* sb = buf + static_cast<size_t>(stage) * sstride;
+        const uint32_t wbytes = static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T));
+        mbar_expect_tx(&full[stage], vbytes + wbytes);
+        if (ncols > 0) bulk_g2s(sb, V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[stage]);
+        bulk_g2s(sb + ncols * PASS_T, w + static_cast<size_t>(t) * PASS_T, wbytes, &full[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
     }
+  } else {
+    // ---- consumers
+    int stage = 0;
+    uint32_t phase = 0;
+    int flip = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int gi = t * PASS_T + r;
+      const bool valid = gi < L.n;
+      cd wi{0.0, 0.0};
+      cd v[PASS_CPG];
+      {
+        mbar_wait(&full[stage], phase);
+        const cd* sb = buf + static_cast<size_t>(stage) * sstride;
+        if (valid) wi = sb[ncols * PASS_T + r];
 #pragma unroll
-    for (int c = 0; c < DOT_CHUNK; ++c) {
-      cd acc{0.0, 0.0};
-      cfmac(acc, a0[c], w0);
-      cfmac(acc, a1[c], w1);
-      red[c * nthr + tid] = acc;
+        for (int j = 0; j < PASS_CPG; ++j) {
+          const int c = q * cpg + j;
+          v[j] = (j < cpg && c < ncols && valid) ? sb[c * PASS_T + r] : cd{0.0, 0.0};
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);   // the tile now lives in registers
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+      if (UPDATE && ncols > 0) {
+        cd p0{0.0, 0.0}, p1{0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < PASS_CPG; j += 2) {
+          if (j < cpg) {
+            const int c = q * cpg + j;
+            cfma(p0, v[j], hs[min(c, ncols - 1)]);
+            cfma(p1, v[j + 1], hs[min(c + 1, ncols - 1)]);
+          }
+        }
+        cd* pp = part + flip * PASS_GROUPS * PASS_T;
+        flip ^= 1;
+        pp[q * PASS_T + r] = p0 + p1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // consumer warps only
+        wi = wi - ((pp[r] + pp[PASS_T + r]) + (pp[2 * PASS_T + r] + pp[3 * PASS_T + r]));
+        if (q == 0 && valid) w[gi] = wi;
+      }
+      if (DOTS) {
+#pragma unroll
+        for (int j = 0; j < PASS_CPG; ++j)
+          if (j < cpg) cfmac(acc[j], v[j], wi);
+      } else if (q == 0) {
+        nrm += abs2(wi);
+      }
     }
+    if (DOTS) {
+      // rows -> one value per (CTA, column): lanes, then the two warps of a column group
+#pragma unroll
+      for (int j = 0; j < PASS_CPG; ++j) {
+        if (j < cpg) {
+          acc[j].x = warp_sum(acc[j].x);
+          acc[j].y = warp_sum(acc[j].y);
+        }
+      }
+      cd* xw = part;   // [8 warps][PASS_CPG]
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < PASS_CPG; ++j) xw[warp * PASS_CPG + j] = acc[j];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = tid; e < PASS_GROUPS * cpg; e += 256) {
+        const int qq = e / cpg, j = e - qq * cpg;
+        const int c = qq * cpg + j;
+        if (c < ncols)
+          partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + c] = xw[(2 * qq) * PASS_CPG + j] + xw[(2 * qq + 1) * PASS_CPG + j];
+      }
+    } else {
+      nrm = warp_sum(nrm);
+      if (lane == 0) red[warp] = nrm;
+    }
+  }
+  if (!DOTS) {
     __syncthreads();
-    if (warp < DOT_CHUNK && cb + warp < ncols) {
-      cd s{0.0, 0.0};
-      for (int k = lane; k < nthr; k += 32) s += red[warp * nthr + k];
-      s.x = warp_sum(s.x);
-      s.y = warp_sum(s.y);
-      if (lane == 0) partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + cb + warp] = s;
-    }
-    if (nwarps < DOT_CHUNK) {   // small tiles: fewer warps than columns in a chunk
-      for (int c = nwarps + warp; c < DOT_CHUNK && cb + c < ncols; c += nwarps) {
+    if (tid == 0) partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + KRYLOV_MAXCOL] = cd{red[0] + red[1], 0.0};
+  }
+  if (last_block_done(ticket, true)) {
+    if (DOTS) {
+      // one warp per column: lanes stride over the CTA partials, fixed-order shuffle tree
+      for (int c = warp; c < ncols; c += PASS_THREADS / 32) {
         cd s{0.0, 0.0};
-        for (int k = lane; k < nthr; k += 32) s += red[c * nthr + k];
+        for (unsigned int b = lane; b < gridDim.x; b += 32) s += partial[static_cast<size_t>(b) * PSTRIDE + c];
         s.x = warp_sum(s.x);
         s.y = warp_sum(s.y);
-        if (lane == 0) partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + cb + c] = s;
+        if (lane == 0) {
+          hwork[c] = s;
+          if (Hcol) Hcol[c] = accumulate ? Hcol[c] + s : s;
+        }
       }
-    }
-    __syncthreads();
-  }
-  if (last_block_done(ticket, lane == 0)) {
-    // one warp per column: lanes stride over the CTA partials, fixed-order shuffle tree
-    for (int c = warp; c < ncols; c += nwarps) {
-      cd s{0.0, 0.0};
-      for (unsigned int b = lane; b < gridDim.x; b += 32) s += partial[static_cast<size_t>(b) * PSTRIDE + c];
-      s.x = warp_sum(s.x);
-      s.y = warp_sum(s.y);
-      if (lane == 0) {
-        hwork[c] = s;
-        if (Hcol) Hcol[c] = accumulate ? Hcol[c] + s : s;
-      }
-    }
-    if (tid == 0) *ticket = 0u;
-  }
-}
-
-// w -= V hwork (STORE) and ||w||^2 ; with ncols == 0 it is a plain norm.
-__global__ void __launch_bounds__(640)
-krylov_update_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, cd* __restrict__ w,
-                     const cd* __restrict__ hwork, cd* __restrict__ partial, double* scal,
-                     unsigned int* ticket) {
-  __shared__ cd hs[KRYLOV_MAXCOL];
-  __shared__ double red[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nthr = blockDim.x, nwarps = nthr >> 5;
-  for (int c = tid; c < ncols; c += nthr) hs[c] = hwork[c];
-  __syncthreads();
-  const int row0 = blockIdx.x * L.T;
-  const int rows = min(L.T, L.n - row0);
-  const cd* tile = V + static_cast<size_t>(blockIdx.x) * L.ncv * L.T;
-  const int i0 = tid, i1 = tid + nthr;
-  const bool ok0 = i0 < rows, ok1 = i1 < rows;
-  cd acc0 = ok0 ? w[row0 + i0] : cd{0.0, 0.0}, acc1 = ok1 ? w[row0 + i1] : cd{0.0, 0.0};
-  for (int cb = 0; cb < ncols; cb += DOT_CHUNK) {
-    cd a0[DOT_CHUNK], a1[DOT_CHUNK];
-#pragma unroll
-    for (int c = 0; c < DOT_CHUNK; ++c) {
-      const bool okc = cb + c < ncols;
-      const cd* col = tile + static_cast<size_t>(cb + c) * L.T;
-      a0[c] = (okc && ok0) ? ldg_cd(col + i0) : cd{0.0, 0.0};
-      a1[c] = (okc && ok1) ? ldg_cd(col + i1) : cd{0.0, 0.0};
-    }
-#pragma unroll
-    for (int c = 0; c < DOT_CHUNK; ++c) {
-      const cd h = cb + c < ncols ? hs[cb + c] : cd{0.0, 0.0};
-      cfms(acc0, a0[c], h);
-      cfms(acc1, a1[c], h);
-    }
-  }
-  double nrm = 0.0;
-  if (ok0) { if (ncols > 0) w[row0 + i0] = acc0; nrm += abs2(acc0); }
-  if (ok1) { if (ncols > 0) w[row0 + i1] = acc1; nrm += abs2(acc1); }
-  nrm = warp_sum(nrm);
-  if (lane == 0) red[warp] = nrm;
-  __syncthreads();
-  if (tid == 0) {
-    double s = 0.0;
-    for (int k = 0; k < nwarps; ++k) s += red[k];
-    partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + KRYLOV_MAXCOL] = cd{s, 0.0};
-  }
-  if (last_block_done(ticket, tid == 0)) {
-    if (warp == 0) {
+    } else if (warp == 0) {
       double s = 0.0;
       for (unsigned int b = lane; b < gridDim.x; b += 32)
         s += partial[static_cast<size_t>(b) * PSTRIDE + KRYLOV_MAXCOL].x;
       s = warp_sum(s);
-      if (lane == 0) {
-        scal[0] = sqrt(s);
-        *ticket = 0u;
-      }
+      if (lane == 0) scal[0] = sqrt(s);
     }
+    __syncthreads();
+    if (tid == 0) *ticket = 0u;
   }
 }
 
@@ -234,6 +270,15 @@ vec_axpby_kernel(int n, cd a, cd* __restrict__ r, cd b, const cd* __restrict__ v
 }  // namespace
 
 BasisLayout make_basis_layout(int n, int ncv) {
+  BasisLayout L{};
+  L.n = n;
+  L.ncv = ncv;
+  L.T = KRYLOV_TILE;
+  L.ntiles = (n + L.T - 1) / L.T;
+  return L;
+}
+
+static int sm_count() {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
@@ -241,30 +286,51 @@ BasisLayout make_basis_layout(int n, int ncv) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  BasisLayout L{};
-  L.n = n;
-  L.ncv = ncv;
-  int T = (n + sms - 1) / sms;             // one tile (= one CTA of T/2 threads) per SM
-  T = ((T + 63) / 64) * 64;
-  if (T > KRYLOV_MAX_T) T = KRYLOV_MAX_T;
-  if (T < 64) T = 64;
-  L.T = T;
-  L.ntiles = (n + T - 1) / T;
-  return L;
+  return sms;
+}
+static size_t pass_smem(int ncols, int nstages) {
+  return sizeof(cd) * (static_cast<size_t>(nstages) * (ncols + 1) * PASS_T + 2 * PASS_GROUPS * PASS_T +
+                       KRYLOV_PASS_MAXCOL) + 16 * nstages;
+}
+// columns [c0, c0 + ncols) of the basis in one launch (ncols <= KRYLOV_PASS_MAXCOL)
+template <bool UPDATE, bool DOTS>
+static void launch_pass(const BasisLayout& L, const cd* V, int c0, int ncols, cd* w, const KrylovWork& work,
+                        cd* Hcol, int accumulate, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(krylov_pass_kernel<UPDATE, DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    220 * 1024));
+    configured = true;
+  }
+  int nstages = 6;
+  while (nstages > 2 && pass_smem(ncols, nstages) > 200 * 1024) --nstages;
+  const int grid = std::max(1, std::min(sm_count(), L.ntiles));
+  krylov_pass_kernel<UPDATE, DOTS><<<grid, PASS_THREADS, pass_smem(ncols, nstages), stream>>>(
+      L, V + static_cast<size_t>(c0) * PASS_T, ncols, nstages, w, work.hwork + c0, work.partial, work.hwork + c0,
+      Hcol ? Hcol + c0 : nullptr, accumulate, work.scal, work.ticket);
 }
 
 void krylov_dots(const BasisLayout& L, const cd* V, int ncols, const cd* w, const KrylovWork& work,
                  cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log) {
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(krylov_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sizeof(cd) * DOT_CHUNK * 640)));
-    configured = true;
-  }
   log->begin(LK_DOTS, 16.0 * L.n * (ncols + 1));
-  const int nthr = L.T / 2;
-  krylov_dots_kernel<<<L.ntiles, nthr, sizeof(cd) * DOT_CHUNK * nthr, stream>>>(L, V, ncols, w, work.partial, work.hwork, Hcol,
-                                                  accumulate, work.ticket);
+  for (int c0 = 0; c0 < ncols; c0 += KRYLOV_PASS_MAXCOL) {
+    launch_pass<false, true>(L, V, c0, std::min(KRYLOV_PASS_MAXCOL, ncols - c0), const_cast<cd*>(w), work, Hcol,
+                             accumulate, stream);
+    log->launches += 1;
+  }
+  log->end();
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void krylov_update_dots(const BasisLayout& L, const cd* V, int ncols, cd* w, const KrylovWork& work,
+                        cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log) {
+  if (ncols > KRYLOV_PASS_MAXCOL) {   // wide basis: the projection needs the fully corrected w
+    krylov_update(L, V, ncols, w, work, stream, log);
+    krylov_dots(L, V, ncols, w, work, Hcol, accumulate, stream, log);
+    return;
+  }
+  log->begin(LK_DOTS, 16.0 * L.n * (ncols + 2));
+  launch_pass<true, true>(L, V, 0, ncols, w, work, Hcol, accumulate, stream);
   log->end();
   log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
@@ -273,10 +339,13 @@ void krylov_dots(const BasisLayout& L, const cd* V, int ncols, const cd* w, cons
 void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const KrylovWork& work,
                    cudaStream_t stream, LaunchLog* log) {
   log->begin(LK_UPDATE, 16.0 * L.n * (ncols + 2));
-  krylov_update_kernel<<<L.ntiles, L.T / 2, 0, stream>>>(L, V, ncols, w, work.hwork, work.partial,
-                                                    work.scal, work.ticket);
+  int c0 = 0;
+  do {   // the last launch leaves ||w|| in scal[0]
+    launch_pass<true, false>(L, V, c0, std::min(KRYLOV_PASS_MAXCOL, ncols - c0), w, work, nullptr, 0, stream);
+    log->launches += 1;
+    c0 += KRYLOV_PASS_MAXCOL;
+  } while (c0 < ncols);
   log->end();
-  log->launches += 1;
   CUDA_CHECK(cudaGetLastError());
 }
 

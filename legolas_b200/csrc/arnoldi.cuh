@@ -11,9 +11,10 @@
 // streams, ~25 % of the copy bandwidth measured).  Here V is tiled by rows: tile t holds
 // rows [t*T, (t+1)*T) of ALL columns contiguously,
 //       V(i, c)  at  ((i / T) * ncv + c) * T + i % T ,
-// so a CTA that owns a tile streams one contiguous T*ncv*16-byte region; T is chosen so that
-// there is one tile per SM and the CTA has T/2 threads (two rows per thread, equal work).  Only the library sees this layout: start vector, operator
-// input and Ritz vectors are plain contiguous vectors.
+// with T = 64: the first j columns of a tile are ONE contiguous block of j KB (a single bulk
+// copy), and a CTA that owns a range of consecutive tiles streams one contiguous region of HBM.
+// Only the library sees this layout: start vector, operator input and Ritz vectors are plain
+// contiguous vectors.
 #pragma once
 
 #include <cstdint>
@@ -23,7 +24,8 @@
 namespace lgpu {
 
 constexpr int KRYLOV_MAXCOL = 128;   // ncv limit of the device kernels
-constexpr int KRYLOV_MAX_T = 1280;   // rows per tile (two rows per thread, <= 640 threads)
+constexpr int KRYLOV_TILE = 64;          // rows per tile
+constexpr int KRYLOV_PASS_MAXCOL = 64;   // columns one Gram-Schmidt pass launch covers
 
 struct BasisLayout {
   int n;        // rows
@@ -46,6 +48,10 @@ struct KrylovWork {
 // or `+=` (accumulate == 1).
 void krylov_dots(const BasisLayout& L, const cd* V, int ncols, const cd* w, const KrylovWork& work,
                  cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log);
+// w -= V(:, 0:ncols) hwork, then hwork = V(:, 0:ncols)^H w in the same pass over V (the middle
+// pass of CGS2); Hcol as in krylov_dots
+void krylov_update_dots(const BasisLayout& L, const cd* V, int ncols, cd* w, const KrylovWork& work,
+                        cd* Hcol, int accumulate, cudaStream_t stream, LaunchLog* log);
 // w -= V(:, 0:ncols) hwork ; afterwards scal[0] = ||w||_2   (ncols == 0: just the norm)
 void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const KrylovWork& work,
                    cudaStream_t stream, LaunchLog* log);
