@@ -99,6 +99,8 @@ struct lgpu_ctx {
   BasisLayout basis{};
   DevBuf<double> kscal;
   DevBuf<unsigned int> kticket;
+  DevBuf<unsigned long long> kgbar;
+  unsigned long long kgbar_count = 0;
   PinnedBuf<cd> h_stage;
   PinnedBuf<double> h_scal;
 
@@ -149,12 +151,15 @@ void ensure_vectors(lgpu_ctx* c) {
 void ensure_krylov_work(lgpu_ctx* c) {
   // one partial row per tile of the basis (dot / update kernels run one CTA per tile)
   const size_t tiles = static_cast<size_t>(make_basis_layout(c->N, 1).ntiles);
-  c->kpartial.ensure(tiles * (KRYLOV_MAXCOL + 1));
+  c->kpartial.ensure((3 * tiles + 8) * (KRYLOV_MAXCOL + 1));   // three partial sets for the fused step
   c->khwork.ensure(KRYLOV_MAXCOL + 1);
   if (!c->kscal.p) {
     c->kscal.ensure(4);
     c->kticket.ensure(1);
     CUDA_CHECK(cudaMemsetAsync(c->kticket.p, 0, sizeof(unsigned int), c->stream));
+    c->kgbar.ensure(1);
+    CUDA_CHECK(cudaMemsetAsync(c->kgbar.p, 0, sizeof(unsigned long long), c->stream));
+    c->kgbar_count = 0;
   }
   c->h_scal.ensure(4);
 }
@@ -162,6 +167,7 @@ void ensure_krylov_work(lgpu_ctx* c) {
 KrylovWork kwork(lgpu_ctx* c) {
   KrylovWork w{};
   w.partial = c->kpartial.p; w.hwork = c->khwork.p; w.scal = c->kscal.p; w.ticket = c->kticket.p;
+  w.gbar = c->kgbar.p; w.gbar_count = &c->kgbar_count;
   return w;
 }
 
@@ -334,14 +340,26 @@ class CudaKrylovOps final : public KrylovOps {
     const BasisLayout& L = c_->basis;
     (void)n;
     if (k == 0) krylov_update(L, V, 0, c_->resid.p, kw, c_->stream, &c_->log);   // rnorm = ||resid||
+    bool have_vj = false;   // did the previous step already normalise v_j into V(:, j) and vcur?
     for (int j = k; j < m; ++j) {
-      cd* hsub = j > 0 ? H + static_cast<size_t>(j - 1) * ncv_ + j : nullptr;
-      krylov_scale(L, c_->resid.p, V, j, c_->vcur.p, kw, hsub, c_->stream, &c_->log);
+      if (!have_vj) {
+        cd* hsub = j > 0 ? H + static_cast<size_t>(j - 1) * ncv_ + j : nullptr;
+        krylov_scale(L, c_->resid.p, V, j, c_->vcur.p, kw, hsub, c_->stream, &c_->log);
+      }
       dev_apply_op(c_, c_->vcur.p, c_->resid.p, refine_);
       cd* hcol = H + static_cast<size_t>(j) * ncv_;
-      krylov_dots(L, V, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->log);
-      krylov_update_dots(L, V, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
-      krylov_update(L, V, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
+      // the fused step also produces v_{j+1} when there is a next step in this batch
+      const int newcol = j + 1 < m ? j + 1 : -1;
+      cd* hnext = H + static_cast<size_t>(j) * ncv_ + j + 1;
+      have_vj = krylov_cgs2_step(L, V, j + 1, c_->resid.p, kw, hcol, newcol, c_->vcur.p, hnext, c_->stream,
+                                 &c_->log);
+      if (have_vj) {
+        have_vj = newcol >= 0;
+      } else {
+        krylov_dots(L, V, j + 1, c_->resid.p, kw, hcol, 0, c_->stream, &c_->log);
+        krylov_update_dots(L, V, j + 1, c_->resid.p, kw, hcol, 1, c_->stream, &c_->log);
+        krylov_update(L, V, j + 1, c_->resid.p, kw, c_->stream, &c_->log);
+      }
     }
   }
 

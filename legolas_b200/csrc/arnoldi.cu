@@ -6,6 +6,7 @@
 #include "arnoldi.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace lgpu {
 namespace {
@@ -204,6 +205,249 @@ krylov_pass_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, int nstag
   }
 }
 
+// ---- one cooperative launch per Arnoldi step ------------------------------------------------
+// The three passes above and the normalisation of the new basis vector as ONE kernel (grid = one
+// CTA per SM, co-resident): between the passes the CTAs meet at a device-wide barrier (a
+// monotonic counter), every CTA sums the per-CTA partials in the same fixed order, and the
+// producer warp keeps streaming the next pass's tiles while the consumers wait (V does not
+// change during the step).  The CTA's rows of w stay in shared memory from the first pass to the
+// normalisation.  Saves three launches and their fill/drain per step and two passes over w.
+struct CgsArgs {
+  BasisLayout L;
+  cd* V;
+  int ncols;
+  int nstages;
+  int tiles_max;                 // rows of wkeep / 64
+  cd* w;                         // in: OP v_j ; out: the orthogonalised residual
+  cd* partial;                   // 3 x gridDim x PSTRIDE
+  cd* Hcol;                      // H(0:ncols, j) = h + s
+  double* scal;                  // scal[0] = || w ||
+  unsigned long long* gbar;      // device-wide barrier counter (monotonic)
+  unsigned long long bar_base;   // its value when this launch starts
+  int newcol;                    // >= 0: V(:, newcol) = vplain = w / ||w|| and *hsub = ||w||
+  cd* vplain;
+  cd* hsub;
+};
+
+__device__ __forceinline__ void cgs_grid_barrier(unsigned long long* ctr, unsigned long long target) {
+  __threadfence();
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (threadIdx.x == 0) {
+    atomicAdd(ctr, 1ULL);
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  __threadfence();
+}
+
+__device__ __forceinline__ cd ldcg_cd(const cd* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return cd{v.x, v.y};
+}
+
+// every CTA: hs[c] = sum over CTAs of partial[b][c], fixed order (consumer warps, one column each)
+__device__ __forceinline__ void cgs_sum_partials(const cd* partial, int ncols, cd* hs, int warp, int lane) {
+  for (int c = warp; c < ncols; c += 8) {
+    cd s{0.0, 0.0};
+    for (unsigned int b = lane; b < gridDim.x; b += 32) s += ldcg_cd(partial + static_cast<size_t>(b) * PSTRIDE + c);
+    s.x = warp_sum(s.x);
+    s.y = warp_sum(s.y);
+    if (lane == 0) hs[c] = s;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __grid_constant__ CgsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const BasisLayout& L = a.L;
+  const int ncols = a.ncols, nstages = a.nstages;
+  const int sstride = (ncols + 1) * PASS_T;
+  cd* buf = reinterpret_cast<cd*>(smem_raw);                            // [nstages][sstride]
+  cd* wkeep = buf + static_cast<size_t>(nstages) * sstride;              // [tiles_max][64]
+  cd* part = wkeep + static_cast<size_t>(a.tiles_max) * PASS_T;          // [2][4][64]
+  cd* hs = part + 2 * PASS_GROUPS * PASS_T;                             // [KRYLOV_PASS_MAXCOL]
+  uint64_t* full = reinterpret_cast<uint64_t*>(hs + KRYLOV_PASS_MAXCOL);
+  uint64_t* empty = full + nstages;
+  __shared__ double red[8];
+  __shared__ double s_norm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = static_cast<int>(static_cast<long long>(blockIdx.x) * L.ntiles / gridDim.x);
+  const int t1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * L.ntiles / gridDim.x);
+  const int nt = t1 - t0;
+  if (tid == 0) {
+    for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 8) {
+    // ---- producer (one lane): three passes over the CTA's tiles through one ring; only the
+    // first pass needs w from global memory
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncols * PASS_T);
+      for (int u = 0; u < 3 * nt; ++u) {
+        const int t = t0 + u % nt;
+        if (u >= nstages) mbar_wait(&empty[stage], phase ^ 1u);
+        cd* sb = buf + static_cast<size_t>(stage) * sstride;
+        const uint32_t wbytes = u < nt ? static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T)) : 0u;
+        mbar_expect_tx(&full[stage], vbytes + wbytes);
+        bulk_g2s(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[stage]);
+        if (wbytes) bulk_g2s(sb + ncols * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+  // ---- consumers: 64 rows x 4 column groups
+  const int cpg = (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
+  const int r = tid & (PASS_T - 1), q = tid >> 6;
+  int stage = 0;
+  uint32_t phase = 0;
+  int flip = 0;
+  cd acc[PASS_CPG];
+  cd v[PASS_CPG];
+  cd* xw = part;   // [8 warps][PASS_CPG] scratch of the row reduction
+
+  auto load_tile = [&](int t, bool want_w, cd& wi) {
+    const bool valid = t * PASS_T + r < L.n;
+    mbar_wait(&full[stage], phase);
+    const cd* sb = buf + static_cast<size_t>(stage) * sstride;
+    if (want_w) wi = valid ? sb[ncols * PASS_T + r] : cd{0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < PASS_CPG; ++j) {
+      const int c = q * cpg + j;
+      v[j] = (j < cpg && c < ncols && valid) ? sb[c * PASS_T + r] : cd{0.0, 0.0};
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);   // the tile now lives in registers
+    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+  };
+  // w_r -= sum_c V(r, c) hs[c] from the registers of the four column groups of row r
+  auto correct = [&](int i) -> cd {
+    cd p0{0.0, 0.0}, p1{0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < PASS_CPG; j += 2) {
+      if (j < cpg) {
+        const int c = q * cpg + j;
+        cfma(p0, v[j], hs[min(c, ncols - 1)]);
+        cfma(p1, v[j + 1], hs[min(c + 1, ncols - 1)]);
+      }
+    }
+    cd* pp = part + flip * PASS_GROUPS * PASS_T;
+    flip ^= 1;
+    pp[q * PASS_T + r] = p0 + p1;
+    const cd wold = wkeep[i * PASS_T + r];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    return wold - ((pp[r] + pp[PASS_T + r]) + (pp[2 * PASS_T + r] + pp[3 * PASS_T + r]));
+  };
+  auto publish_dots = [&](cd* dst) {   // rows -> one value per (CTA, column)
+#pragma unroll
+    for (int j = 0; j < PASS_CPG; ++j) {
+      if (j < cpg) {
+        acc[j].x = warp_sum(acc[j].x);
+        acc[j].y = warp_sum(acc[j].y);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < PASS_CPG; ++j) xw[warp * PASS_CPG + j] = acc[j];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int e = tid; e < PASS_GROUPS * cpg; e += 256) {
+      const int qq = e / cpg, j = e - qq * cpg;
+      const int c = qq * cpg + j;
+      if (c < ncols)
+        dst[static_cast<size_t>(blockIdx.x) * PSTRIDE + c] = xw[(2 * qq) * PASS_CPG + j] + xw[(2 * qq + 1) * PASS_CPG + j];
+    }
+  };
+
+  cd* partial1 = a.partial;
+  cd* partial2 = a.partial + static_cast<size_t>(gridDim.x) * PSTRIDE;
+  cd* partial3 = a.partial + static_cast<size_t>(2 * gridDim.x) * PSTRIDE;
+
+  // ---- pass 1: h = V^H w
+#pragma unroll
+  for (int j = 0; j < PASS_CPG; ++j) acc[j] = cd{0.0, 0.0};
+  for (int i = 0; i < nt; ++i) {
+    cd wi{0.0, 0.0};
+    load_tile(t0 + i, true, wi);
+    if (q == 0) wkeep[i * PASS_T + r] = wi;
+#pragma unroll
+    for (int j = 0; j < PASS_CPG; ++j)
+      if (j < cpg) cfmac(acc[j], v[j], wi);
+  }
+  publish_dots(partial1);
+  cgs_grid_barrier(a.gbar, a.bar_base + gridDim.x);
+  cgs_sum_partials(partial1, ncols, hs, warp, lane);
+  if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = hs[c];
+
+  // ---- pass 2: w -= V h ; s = V^H w
+#pragma unroll
+  for (int j = 0; j < PASS_CPG; ++j) acc[j] = cd{0.0, 0.0};
+  for (int i = 0; i < nt; ++i) {
+    cd wi{0.0, 0.0};
+    load_tile(t0 + i, false, wi);
+    wi = correct(i);
+    if (q == 0) wkeep[i * PASS_T + r] = wi;
+#pragma unroll
+    for (int j = 0; j < PASS_CPG; ++j)
+      if (j < cpg) cfmac(acc[j], v[j], wi);
+  }
+  publish_dots(partial2);
+  cgs_grid_barrier(a.gbar, a.bar_base + 2ull * gridDim.x);
+  cgs_sum_partials(partial2, ncols, hs, warp, lane);
+  if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = a.Hcol[c] + hs[c];
+
+  // ---- pass 3: w -= V s ; || w ||
+  double nrm = 0.0;
+  for (int i = 0; i < nt; ++i) {
+    cd wi{0.0, 0.0};
+    load_tile(t0 + i, false, wi);
+    wi = correct(i);
+    if (q == 0) {
+      wkeep[i * PASS_T + r] = wi;
+      const int gi = (t0 + i) * PASS_T + r;
+      if (gi < L.n) { a.w[gi] = wi; nrm += abs2(wi); }
+    }
+  }
+  nrm = warp_sum(nrm);
+  if (lane == 0) red[warp] = nrm;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid == 0) partial3[static_cast<size_t>(blockIdx.x) * PSTRIDE] = cd{red[0] + red[1], 0.0};
+  cgs_grid_barrier(a.gbar, a.bar_base + 3ull * gridDim.x);
+  if (warp == 0) {
+    double s = 0.0;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) s += ldcg_cd(partial3 + static_cast<size_t>(b) * PSTRIDE).x;
+    s = warp_sum(s);
+    if (lane == 0) s_norm = sqrt(s);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const double rnorm = s_norm;
+  if (blockIdx.x == 0 && tid == 0) {
+    a.scal[0] = rnorm;
+    if (a.newcol >= 0 && a.hsub) *a.hsub = cd{rnorm, 0.0};
+  }
+  // ---- the next basis vector: V(:, newcol) = vplain = w / ||w||
+  if (a.newcol >= 0) {
+    const double inv = 1.0 / rnorm;
+    for (int e = tid; e < nt * PASS_T; e += 256) {
+      const int i = e >> 6, rr = e & (PASS_T - 1);
+      const int gi = (t0 + i) * PASS_T + rr;
+      if (gi < L.n) {
+        const cd x = wkeep[e] * inv;
+        a.V[(static_cast<size_t>(t0 + i) * L.ncv + a.newcol) * PASS_T + rr] = x;
+        a.vplain[gi] = x;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ size_t basis_off(const BasisLayout& L, int i, int c) {
   const int t = i / L.T;
   return (static_cast<size_t>(t) * L.ncv + c) * L.T + (i - t * L.T);
@@ -347,6 +591,41 @@ void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const Kr
   } while (c0 < ncols);
   log->end();
   CUDA_CHECK(cudaGetLastError());
+}
+
+static size_t cgs2_smem(int ncols, int nstages, int tiles_max) {
+  return sizeof(cd) * (static_cast<size_t>(nstages) * (ncols + 1) * PASS_T + static_cast<size_t>(tiles_max) * PASS_T +
+                       2 * PASS_GROUPS * PASS_T + KRYLOV_PASS_MAXCOL) + 16 * nstages;
+}
+
+bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const KrylovWork& work, cd* Hcol,
+                      int newcol, cd* vplain, cd* hsub, cudaStream_t stream, LaunchLog* log) {
+  static const bool enabled = [] { const char* e = std::getenv("LGPU_CGS2_FUSED"); return !(e && e[0] == '0'); }();
+  const int grid = std::max(1, std::min(sm_count(), L.ntiles));
+  const int tiles_max = (L.ntiles + grid - 1) / grid;
+  int nstages = 5;
+  while (nstages > 2 && cgs2_smem(ncols, nstages, tiles_max) > 210 * 1024) --nstages;
+  if (!enabled || ncols < 1 || ncols > KRYLOV_PASS_MAXCOL || work.gbar == nullptr ||
+      cgs2_smem(ncols, nstages, tiles_max) > 210 * 1024)
+    return false;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  CgsArgs a{};
+  a.L = L; a.V = V; a.ncols = ncols; a.nstages = nstages; a.tiles_max = tiles_max; a.w = w;
+  a.partial = work.partial; a.Hcol = Hcol; a.scal = work.scal; a.gbar = work.gbar;
+  a.bar_base = *work.gbar_count;
+  *work.gbar_count += 3ull * grid;
+  a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
+  void* args[] = {&a};
+  log->begin(LK_DOTS, 16.0 * L.n * (3.0 * ncols + 4.0));
+  CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(krylov_cgs2_kernel), dim3(grid), dim3(PASS_THREADS),
+                                         args, cgs2_smem(ncols, nstages, tiles_max), stream));
+  log->end();
+  log->launches += 1;
+  return true;
 }
 
 void krylov_scale(const BasisLayout& L, const cd* w, cd* V, int col, cd* vplain,

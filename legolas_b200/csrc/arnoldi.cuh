@@ -42,6 +42,8 @@ struct KrylovWork {
   cd* hwork;          // [KRYLOV_MAXCOL + 1] coefficients of the current projection
   double* scal;       // [0] rnorm  [1] scratch
   unsigned int* ticket;
+  unsigned long long* gbar;         // device-wide barrier counter of the fused step kernel (or null)
+  unsigned long long* gbar_count;   // host: value the counter will have when the next launch starts
 };
 
 // h = V(:, 0:ncols)^H w  -> work.hwork ; Hcol (device, may be null) gets `=` (accumulate == 0)
@@ -55,6 +57,13 @@ void krylov_update_dots(const BasisLayout& L, const cd* V, int ncols, cd* w, con
 // w -= V(:, 0:ncols) hwork ; afterwards scal[0] = ||w||_2   (ncols == 0: just the norm)
 void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const KrylovWork& work,
                    cudaStream_t stream, LaunchLog* log);
+// One whole CGS2 step in a single cooperative launch: Hcol = h + s with h = V^H w, w -= V h,
+// s = V^H w, w -= V s ; scal[0] = ||w|| ; if newcol >= 0 also V(:, newcol) = vplain = w / ||w|| and
+// *hsub = ||w||.  Returns false (nothing launched) when the step does not fit this path (basis
+// wider than KRYLOV_PASS_MAXCOL columns, more rows than one resident wave can keep on chip):
+// the caller then runs the three pass kernels and krylov_scale.
+bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const KrylovWork& work, cd* Hcol,
+                      int newcol, cd* vplain, cd* hsub, cudaStream_t stream, LaunchLog* log);
 // V(:, col) = vplain = w / scal[0] ; if hsub != null: *hsub = (scal[0], 0)
 void krylov_scale(const BasisLayout& L, const cd* w, cd* V, int col, cd* vplain,
                   const KrylovWork& work, cd* hsub, cudaStream_t stream, LaunchLog* log);
