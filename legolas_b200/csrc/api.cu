@@ -14,6 +14,7 @@
 #include "arnoldi.cuh"
 #include "assemble.cuh"
 #include "slu.cuh"
+#include "bsparse.cuh"
 #include "common.cuh"
 #include "iram.hpp"
 
@@ -87,6 +88,9 @@ struct lgpu_ctx {
   SluPlan splan;
   DevBuf<cd> pairs, topfac, fwork, rhs, gvec, xpad;
   DevBuf<int32_t> d_info;
+  DevBuf<cd> bell_val;          // compressed copy of B for the operator application
+  DevBuf<int32_t> bell_col, bell_width;
+  int bell_w = -1;              // longest row of B; -1: not built for the current B
   DevBuf<unsigned long long> d_sync;
   unsigned long long solve_epoch = 0;
   bool factorized = false;
@@ -244,6 +248,7 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
   CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->t_assemble = ms;
   c->have[0] = c->have[1] = true;
+  c->bell_w = -1;
   return LGPU_OK;
 }
 
@@ -290,9 +295,18 @@ int do_factorize(lgpu_ctx* c, cd sigma) {
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
   slu_factorize(c->splan, c->sdev(), sigma, c->stream, &c->log);
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
-  int32_t info = 0;
+  int32_t info = 0, bwidth = c->bell_w;
+  if (c->bell_w < 0) {   // B changed since the last factorisation: refresh its compressed copy
+    const size_t rows = static_cast<size_t>(c->N);
+    c->bell_val.ensure(rows * ELL_MAX_WIDTH);
+    c->bell_col.ensure(rows * ELL_MAX_WIDTH);
+    c->bell_width.ensure(1);
+    bell_build(c->G, c->B.p, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->stream, &c->log);
+    CUDA_CHECK(cudaMemcpyAsync(&bwidth, c->bell_width.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   CUDA_CHECK(cudaMemcpyAsync(&info, c->d_info.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->bell_w = bwidth;
   float ms = 0.f;
   CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->t_factor = ms;
@@ -321,8 +335,13 @@ void dev_solve(lgpu_ctx* c, const cd* b, cd* x, int refine) {
 
 // y = M^-1 B x on the device (x, y may alias)
 void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
-  block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, c->vu.p, c->stream,
-               &c->log);
+  static const bool use_ell = [] { const char* e = std::getenv("LGPU_B_ELL"); return !(e && e[0] == '0'); }();
+  if (use_ell && c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
+    bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->bell_w, x, c->vu.p, c->stream,
+                &c->log);
+  else
+    block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, c->vu.p, c->stream,
+                 &c->log);
   dev_solve(c, c->vu.p, y, refine);
 }
 
@@ -722,6 +741,7 @@ int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const 
     CUDA_CHECK(cudaMemcpy(ctx->masks.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemset(ctx->natmasks.p, 0, (2 * 2 * 4 * 8 + 2) * sizeof(uint32_t)));
     ctx->have[which] = true;
+    if (which == 1) ctx->bell_w = -1;
     return LGPU_OK;
   });
 }

@@ -103,7 +103,7 @@ class Iram {
       res.n_op += kplusp - kcur;
       res.n_reorth += kplusp - kcur;
       // zneigh: Ritz values and error bounds of the current H
-      if (neigh(kplusp, rnorm, T, Q, ritz, bounds) != 0) { res.info = -8; return res; }
+      if (neigh(kplusp, rnorm, T, Q, ritz, bounds, false) != 0) { res.info = -8; return res; }
       ritz0 = ritz;
       bounds0 = bounds;
       nev = nev0;
@@ -145,6 +145,9 @@ class Iram {
                    t_enq, t_wait, t_dense, t_compress, iter);
     res.n_iter = iter;
     res.nconv = std::min(nconv, nev0);
+    // Schur form of the final H with all of Q (ritz / bounds of the loop's last pass stay in
+    // ritz0 / bounds0)
+    if (res.nconv > 0 && neigh(kplusp, rnorm, T, Q, ritz, bounds, true) != 0) { res.info = -8; return res; }
     extract(ops, cfg, kplusp, nev0, np0, res.nconv, tol, eps23, rnorm, ritz0, bounds0, T, Q, res);
     return res;
   }
@@ -155,24 +158,36 @@ class Iram {
   static bool H0norm_ok(double rnorm) { return rnorm > 0.0 && std::isfinite(rnorm); }
 
   cplx& h(int i, int j, int ld) { return H_[static_cast<size_t>(j) * ld + i]; }
+  std::vector<cplx> qrow_, X_;
 
   // zneigh
+  // The error bounds need only the last row of the Schur vectors, and the rotations act on the
+  // rows of Q independently: inside the restart loop only that row is accumulated (1 x n matrix,
+  // same arithmetic as the last row of the full accumulation); the full Q is formed once, for
+  // the final H, before the Ritz vectors are extracted (full_q).
   int neigh(int n, double rnorm, std::vector<cplx>& T, std::vector<cplx>& Q,
-            std::vector<cplx>& ritz, std::vector<cplx>& bounds) {
+            std::vector<cplx>& ritz, std::vector<cplx>& bounds, bool full_q) {
     const int ld = n;
     T = H_;
-    std::fill(Q.begin(), Q.end(), cplx(0.0));
-    for (int i = 0; i < n; ++i) Q[static_cast<size_t>(i) * ld + i] = 1.0;
-    if (dense::hessenberg_schur(n, T.data(), ld, Q.data(), ld, n, ritz.data()) != 0) return -8;
-    std::vector<cplx> X(static_cast<size_t>(ld) * ld);
-    dense::triangular_eigvecs(n, T.data(), ld, X.data(), ld);
+    qrow_.assign(n, cplx(0.0));
+    qrow_[n - 1] = 1.0;
+    if (full_q) {
+      std::fill(Q.begin(), Q.end(), cplx(0.0));
+      for (int i = 0; i < n; ++i) Q[static_cast<size_t>(i) * ld + i] = 1.0;
+      if (dense::hessenberg_schur(n, T.data(), ld, Q.data(), ld, n, ritz.data()) != 0) return -8;
+      for (int i = 0; i < n; ++i) qrow_[i] = Q[static_cast<size_t>(i) * ld + (n - 1)];
+    } else {
+      if (dense::hessenberg_schur(n, T.data(), ld, qrow_.data(), 1, 1, ritz.data()) != 0) return -8;
+    }
+    X_.resize(static_cast<size_t>(ld) * ld);
+    dense::triangular_eigvecs(n, T.data(), ld, X_.data(), ld);
     // last component of each unit-norm eigenvector of H:  (Q X)(n-1, j) / ||Q X(:, j)||
     for (int j = 0; j < n; ++j) {
       cplx last = 0.0;
       double nrm2 = 0.0;
       for (int i = 0; i <= j; ++i) {
-        last += Q[static_cast<size_t>(i) * ld + (n - 1)] * X[static_cast<size_t>(j) * ld + i];
-        nrm2 += std::norm(X[static_cast<size_t>(j) * ld + i]);   // Q unitary: ||Q x|| = ||x||
+        last += qrow_[i] * X_[static_cast<size_t>(j) * ld + i];
+        nrm2 += std::norm(X_[static_cast<size_t>(j) * ld + i]);   // Q unitary: ||Q x|| = ||x||
       }
       bounds[j] = rnorm * last / std::sqrt(nrm2);
     }
