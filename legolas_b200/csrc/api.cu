@@ -105,7 +105,7 @@ struct lgpu_ctx {
   DevBuf<unsigned int> kticket;
   DevBuf<unsigned long long> kgbar;
   unsigned long long kgbar_count = 0;
-  PinnedBuf<cd> h_stage;
+  PinnedBuf<cd> h_stage, h_upload;
   PinnedBuf<double> h_scal;
 
   LaunchLog log;
@@ -403,15 +403,18 @@ class CudaKrylovOps final : public KrylovOps {
     *rnorm = c_->h_scal.p[0];
   }
 
+  // Upload through a staging buffer of its own: the download staging buffer (fetch) is free to be
+  // rewritten, and the copy enqueued here is complete by the time the host gets back (every
+  // restart passes through the stream synchronisation of the next fetch()).
   void upload_small(const cplx* M, int ld, int rows, int cols) {
     const size_t cnt = static_cast<size_t>(ncv_) * ncv_;
-    c_->h_stage.ensure(cnt);
+    c_->h_upload.ensure(cnt);
     for (int j = 0; j < cols; ++j)
       for (int i = 0; i < rows; ++i) {
         const cplx v = M[static_cast<size_t>(j) * ld + i];
-        c_->h_stage.p[static_cast<size_t>(j) * ncv_ + i] = cd{v.real(), v.imag()};
+        c_->h_upload.p[static_cast<size_t>(j) * ncv_ + i] = cd{v.real(), v.imag()};
       }
-    CUDA_CHECK(cudaMemcpyAsync(c_->Qdev.p, c_->h_stage.p, cnt * sizeof(cd), cudaMemcpyHostToDevice,
+    CUDA_CHECK(cudaMemcpyAsync(c_->Qdev.p, c_->h_upload.p, cnt * sizeof(cd), cudaMemcpyHostToDevice,
                                c_->stream));
   }
 
@@ -424,8 +427,6 @@ class CudaKrylovOps final : public KrylovOps {
     vec_axpby_basis(c_->basis, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
                     c_->V.p, kev, c_->stream, &c_->log);
     krylov_update(c_->basis, c_->V.p, 0, c_->resid.p, kwork(c_), c_->stream, &c_->log);
-    // the staging buffer is reused by the next fetch(): make sure the upload has been consumed
-    CUDA_CHECK(cudaStreamSynchronize(c_->stream));
   }
 
   void ritz_vectors(int kplusp, int nconv, const cplx* S, int lds) override {

@@ -467,6 +467,46 @@ krylov_scale_kernel(BasisLayout L, const cd* __restrict__ w, cd* __restrict__ V,
   if (hsub && i == 0) *hsub = cd{rnorm, 0.0};
 }
 
+// Restart / extraction GEMM, one thread per row: the row of V is pulled into registers with NK
+// independent coalesced loads, every output column is then a dot product against a column of Q
+// broadcast from shared memory (one wavefront per FMA group), so the kernel is bounded by the
+// FP64 pipe and HBM instead of shared-memory traffic; safe in place for any nc (the row is in
+// registers before the first store).  NK = 40 covers ARPACK's default ncv = 2 nev of this path.
+template <int NK>
+__global__ void __launch_bounds__(128)
+basis_gemm_rows_kernel(BasisLayout L, const cd* V, int nk, const cd* __restrict__ Q, int ldq, int nc,
+                       cd* Out, int out_plain_ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* Qs = reinterpret_cast<cd*>(smem_raw);   // [nc][nk]
+  for (int e = threadIdx.x; e < nk * nc; e += 128) {
+    const int j = e % nk, c = e / nk;
+    Qs[e] = Q[static_cast<size_t>(c) * ldq + j];
+  }
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int ic = min(i, L.n - 1);
+  const int t = ic / L.T, r = ic - t * L.T;
+  const cd* row = V + static_cast<size_t>(t) * L.ncv * L.T + r;   // column j at row[j * T]
+  cd v[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) v[j] = j < nk ? row[static_cast<size_t>(j) * L.T] : cd{0.0, 0.0};
+  __syncthreads();
+  if (i >= L.n) return;
+  for (int c = 0; c < nc; ++c) {
+    const cd* q = Qs + c * nk;
+    cd a0{0.0, 0.0}, a1{0.0, 0.0}, a2{0.0, 0.0}, a3{0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < NK; j += 4) {
+      if (j < nk) cfma(a0, v[j], q[j]);
+      if (j + 1 < nk) cfma(a1, v[j + 1], q[j + 1]);
+      if (j + 2 < nk) cfma(a2, v[j + 2], q[j + 2]);
+      if (j + 3 < nk) cfma(a3, v[j + 3], q[j + 3]);
+    }
+    const cd acc = (a0 + a1) + (a2 + a3);
+    if (out_plain_ld > 0) Out[static_cast<size_t>(c) * out_plain_ld + i] = acc;
+    else Out[(static_cast<size_t>(t) * L.ncv + c) * L.T + r] = acc;
+  }
+}
+
 // 32 consecutive rows (inside one tile: T is a multiple of 32) per CTA.
 __global__ void __launch_bounds__(256)
 basis_gemm_kernel(BasisLayout L, const cd* __restrict__ V, int nk, const cd* __restrict__ Q,
@@ -647,7 +687,12 @@ void basis_gemm(const BasisLayout& L, const cd* V, int nk, const cd* Q, int ldq,
     configured = smem;
   }
   log->begin(LK_GEMM, 16.0 * L.n * (nk + nc));
-  basis_gemm_kernel<<<(L.n + 31) / 32, 256, smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld);
+  static const bool rows_path = [] { const char* e = std::getenv("LGPU_GEMM_ROWS"); return !(e && e[0] == '0'); }();
+  if (rows_path && nk <= 40 && sizeof(cd) * nk * nc <= 48 * 1024)
+    basis_gemm_rows_kernel<40><<<(L.n + 127) / 128, 128, sizeof(cd) * nk * nc, stream>>>(L, V, nk, Q, ldq, nc, Out,
+                                                                                         out_plain_ld);
+  else
+    basis_gemm_kernel<<<(L.n + 31) / 32, 256, smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld);
   log->end();
   log->launches += 1;
   CUDA_CHECK(cudaGetLastError());

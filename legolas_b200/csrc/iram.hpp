@@ -78,7 +78,7 @@ class Iram {
 
     using clk = std::chrono::steady_clock;
     auto since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
-    double t_enq = 0, t_wait = 0, t_dense = 0, t_compress = 0;
+    double t_enq = 0, t_wait = 0, t_dense = 0, t_compress = 0, t_neigh = 0;
     const bool trace = std::getenv("LGPU_TRACE") != nullptr;
     ops.init_residual();
     res.n_op = 1;
@@ -103,7 +103,11 @@ class Iram {
       res.n_op += kplusp - kcur;
       res.n_reorth += kplusp - kcur;
       // zneigh: Ritz values and error bounds of the current H
-      if (neigh(kplusp, rnorm, T, Q, ritz, bounds, false) != 0) { res.info = -8; return res; }
+      {
+        const auto tn = clk::now();
+        if (neigh(kplusp, rnorm, T, Q, ritz, bounds, false) != 0) { res.info = -8; return res; }
+        t_neigh += since(tn);
+      }
       ritz0 = ritz;
       bounds0 = bounds;
       nev = nev0;
@@ -141,8 +145,8 @@ class Iram {
       kcur = nev;
     }
     if (trace)
-      std::fprintf(stderr, "[lgpu] iram: enqueue %.2f ms, wait %.2f ms, host dense %.2f ms, compress %.2f ms, restarts %d\n",
-                   t_enq, t_wait, t_dense, t_compress, iter);
+      std::fprintf(stderr, "[lgpu] iram: enqueue %.2f ms, wait %.2f ms, host dense %.2f ms (Ritz values/bounds %.2f), compress %.2f ms, restarts %d\n",
+                   t_enq, t_wait, t_dense, t_neigh, t_compress, iter);
     res.n_iter = iter;
     res.nconv = std::min(nconv, nev0);
     // Schur form of the final H with all of Q (ritz / bounds of the loop's last pass stay in
