@@ -169,9 +169,10 @@ int lgpu_counters(lgpu_ctx* ctx, int64_t* kernel_launches, int32_t reset);
 /* Optional per-kernel-class device timing: CUDA events are recorded on the context's stream
  * around every launch; lgpu_profile_read synchronises and returns the accumulated
  * milliseconds, launch counts and algorithmic bytes per class, in this order (LGPU_N_KINDS entries):
- * assemble, factor, matvec, fwd_stage0, fwd_stage, top_stage, bwd_stage, bwd_stage0, dots,
- * update, scale, gemm, other. */
-#define LGPU_N_KINDS 13
+ * assemble, factor, matvec, fwd_stage0, fwd_stage, top_stage (the fused upper solve stages and the
+ * top system), bwd_stage, bwd_stage0, dots, update, scale, gemm, cgs2_step (the fused
+ * Gram-Schmidt step), other. */
+#define LGPU_N_KINDS 14
 int lgpu_set_profiling(lgpu_ctx* ctx, int32_t enable);
 int lgpu_profile_read(lgpu_ctx* ctx, double* ms, int64_t* counts, double* algo_bytes,
                       int32_t nkinds, int32_t reset);

@@ -239,7 +239,7 @@ class Context:
         return dict(zip(("assemble_ms", "factor_ms", "iter_ms", "extract_ms"), (x.value for x in t)))
 
     KINDS = ("assemble", "factor", "matvec", "fwd_stage0", "fwd_stage", "top_stage", "bwd_stage",
-             "bwd_stage0", "dots", "update", "scale", "gemm", "other")
+             "bwd_stage0", "dots", "update", "scale", "gemm", "cgs2_step", "other")
 
     def set_profiling(self, enable: bool):
         self._check(self._lib.lgpu_set_profiling(self._h, int(enable)), "set_profiling")

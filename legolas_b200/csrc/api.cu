@@ -265,27 +265,6 @@ int do_factorize(lgpu_ctx* c, cd sigma) {
     c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
     c->d_info.ensure(1);
     c->d_sync.ensure(SLU_SYNC_COUNTERS);
-    // Keep the factor records of the narrow upper levels (latency-bound, ~20 MB at G = 10001)
-    // resident in L2: persisting access-policy window on the context's stream.
-    const int nl = static_cast<int>(c->splan.levels.size());
-    const int lsplit = env_int("LGPU_L2_PERSIST_LEVEL", 4);
-    if (lsplit >= 0 && lsplit < nl) {
-      const size_t first = c->splan.levels[lsplit].off_pairs;
-      const size_t bytes = (c->splan.pair_records - first) * PAIR_STRIDE * sizeof(cd);
-      int dev_max = 0;
-      cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-      if (bytes > 0 && dev_max > 0 && bytes <= static_cast<size_t>(dev_max)) {
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
-        cudaStreamAttrValue attr{};
-        attr.accessPolicyWindow.base_ptr = c->pairs.p + first * PAIR_STRIDE;
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = 1.0f;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
-          cudaGetLastError();   // optional optimisation: ignore if unsupported
-      }
-    }
   }
   ensure_vectors(c);
   c->log.stream = c->stream;

@@ -660,7 +660,7 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   *work.gbar_count += 3ull * grid;
   a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
   void* args[] = {&a};
-  log->begin(LK_DOTS, 16.0 * L.n * (3.0 * ncols + 4.0));
+  log->begin(LK_CGS2, 16.0 * L.n * (3.0 * ncols + 4.0));
   CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(krylov_cgs2_kernel), dim3(grid), dim3(PASS_THREADS),
                                          args, cgs2_smem(ncols, nstages, tiles_max), stream));
   log->end();

@@ -82,7 +82,7 @@ inline void cuda_check(cudaError_t err, const char* what, const char* file, int 
 // on the launching stream around each launch; read back at a synchronisation point).
 enum LaunchKind {
   LK_ASSEMBLE = 0, LK_FACTOR, LK_MATVEC, LK_FWD0, LK_FWD, LK_TOP, LK_BWD, LK_BWD0, LK_DOTS,
-  LK_UPDATE, LK_SCALE, LK_GEMM, LK_OTHER, LK_COUNT
+  LK_UPDATE, LK_SCALE, LK_GEMM, LK_CGS2, LK_OTHER, LK_COUNT
 };
 
 // ---- mbarrier + bulk asynchronous copy (TMA without a tensor map), sm_90+ PTX ----------------
@@ -112,6 +112,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// L2 eviction-priority policies for bulk copies (the stream access-policy window does not apply
+// to the async proxy): evict_first for data streamed once per launch, evict_last for the small
+// hot set that every launch re-reads.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 #endif   // __CUDACC__
 

@@ -165,11 +165,11 @@ __device__ __forceinline__ void ring_release(const Ring& rg, RingPos& p, int lan
 // producer lane: next slot of the ring <- `count` complex entries at src.  `p.phase` is the
 // parity of the use being filled; `wrapped` says whether the slot has been used before.
 __device__ __forceinline__ void ring_emit(const Ring& rg, RingPos& p, bool& wrapped, const cd* src,
-                                          int count) {
+                                          int count, uint64_t policy) {
   if (wrapped) mbar_wait(&rg.empty[p.slot], p.phase ^ 1u);
   const uint32_t bytes = static_cast<uint32_t>(count * sizeof(cd));
   mbar_expect_tx(&rg.full[p.slot], bytes);
-  bulk_g2s(rg.slots + p.slot * rg.stride, src, bytes, &rg.full[p.slot]);
+  bulk_g2s_hint(rg.slots + p.slot * rg.stride, src, bytes, &rg.full[p.slot], policy);
   if (p.slot == rg.ns - 1) wrapped = true;
   advance(rg, p);
 }
@@ -177,6 +177,7 @@ __device__ __forceinline__ void ring_emit(const Ring& rg, RingPos& p, bool& wrap
 struct Producer {
   RingPos blk{0, 0u}, u{0, 0u};
   bool blk_wrapped = false, u_wrapped = false;
+  uint64_t policy = 0;   // L2 eviction priority of the records this CTA streams
 };
 
 template <bool FWD>
@@ -189,12 +190,12 @@ __device__ __forceinline__ void ring_produce(const StageArgs& a, const Ring& rg,
     for (int i = 0; i < ml / 2; ++i) {
       const cd* rec = a.pairs + (pair0 + i) * PAIR_STRIDE;
       if (FWD) {
-        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_PERM, PR_L21 - PR_PERM);
-        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_L21, SB2);
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_PERM, PR_L21 - PR_PERM, pr.policy);
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_L21, SB2, pr.policy);
       } else {
-        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_E, SB2);
-        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_F, SB2);
-        ring_emit(ur, pr.u, pr.u_wrapped, rec + PR_U, TRI);
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_E, SB2, pr.policy);
+        ring_emit(rg, pr.blk, pr.blk_wrapped, rec + PR_F, SB2, pr.policy);
+        ring_emit(ur, pr.u, pr.u_wrapped, rec + PR_U, TRI, pr.policy);
       }
     }
   }
@@ -487,6 +488,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArg
   if (threadIdx.x >= NCW * 32) {
     if (threadIdx.x == NCW * 32) {
       Producer pr;
+      pr.policy = gridDim.x > 148 ? l2_policy_evict_first() : l2_policy_evict_last();
       const int r0 = blockIdx.x * C;
       ring_produce<true>(a, rg, rg, pr, r0, min(C, a.m0 - r0));
     }
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
   if (threadIdx.x >= NCW * 32) {
     if (threadIdx.x == NCW * 32) {
       Producer pr;
+      pr.policy = gridDim.x > 148 ? l2_policy_evict_first() : l2_policy_evict_last();
       const int r0 = blockIdx.x * C;
       ring_produce<false>(a, rg, ur, pr, r0, min(C, a.m0 - r0));
     }
@@ -574,6 +577,7 @@ __global__ void __launch_bounds__(RING_THREADS) slu_fused_stage_kernel(const __g
   if (tid >= NCW * 32) {
     if (tid == NCW * 32) {
       Producer pr;
+      pr.policy = l2_policy_evict_last();   // the upper levels: a few MB that every solve re-reads
       for (int s = 0; s < top; ++s) {
         const StageArgs& a = f.st[s];
         const int C = 1 << a.mu;
@@ -636,6 +640,7 @@ __global__ void __launch_bounds__(RING_THREADS) slu_top_stage_kernel(StageArgs a
   if (tid >= NCW * 32) {
     if (tid == NCW * 32 && a.m0 > 0) {
       Producer pr;
+      pr.policy = l2_policy_evict_last();
       ring_produce<true>(a, rg, ur, pr, 0, a.m0);
       ring_produce<false>(a, rg, ur, pr, 0, a.m0);
     }
