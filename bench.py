@@ -37,9 +37,12 @@ METRIC = "time to 20 shift-invert eigenpairs at 10k gridpts"
 UNIT = "s"
 GRIDPTS = 10001
 NEV = 20
-# 8-shift spectrum scan of config 4; rank r takes SHIFTS[r % 8]
-SHIFTS = [0.02 + 0.03j, 0.02 + 0.045j, 0.018 + 0.024j, 0.015 + 0.018j, 0.028j, 0.006 + 0.017j,
-          -0.02 + 0.03j, -0.02 + 0.045j]
+# 8-shift scan of config 4 around the headline shift (rank r takes SHIFTS[r % 8]).  All eight
+# converge to nev = 20 in 14-17 restarts (176-209 operator applications, scripts/shift_scan.py),
+# so the per-GPU work of the weak-scaling run is the same to ~10 %; shifts further out
+# (0.02+0.045i, 0.028i, 0.006+0.017i) sit inside accumulation continua and stop at maxiter.
+SHIFTS = [0.02 + 0.03j, 0.021 + 0.031j, 0.019 + 0.029j, 0.02 + 0.032j, 0.0205 + 0.03j, 0.0195 + 0.031j,
+          0.021 + 0.029j, 0.02 + 0.028j]
 WORKLOAD = ("magnetothermal_instabilities cylindrical G=10001 (N=160016), k2=0 k3=1, Rosner cooling + "
             "thermal-balance heating + parallel conduction, shift-invert nev=20 ncv=40 tol=5e-15 "
             "maxiter=200, start vector zlarnv(2,[2022,9,30,179])")
