@@ -160,6 +160,22 @@ int lgpu_shift_invert_device(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const doubl
 void* lgpu_host_alloc(size_t bytes);
 void lgpu_host_free(void* ptr);
 
+/* ---- rows N1 / N4 of the scope table (consumers of the factorisation and the matvecs) -------
+ * residuals: res[k] = || A v_k - omega_k B v_k ||_2 / || omega_k v_k ||_2, 0 where omega_k is zero
+ *            by the reference's is_zero rule (get_residual, src/dataIO/mod_output.f08:511-545);
+ *            vr_ri: N x nev complex host, ld = N.
+ * inverse_iteration: replaces inverse_iteration (src/solvers/smod_inverse_iteration.f08:16-205):
+ *            LU of A - sigma B, then x <- normalised (A - sigma B)^-1 B x until
+ *            || A x - ev B x || < |ev| tol with ev = x^H A x / x^H B x, at most maxiter solves
+ *            (0 = the reference's default 100).  omega_ri: 1 complex; vr_ri: N complex, largest
+ *            entry made real, or NULL; stats->info = 0 converged, 1 maxiter reached;
+ *            stats->n_op = solves.  Deviation: the start vector is (A - sigma B)^-1 1 instead of
+ *            LAPACK's U^-1 1 (the factors are not LAPACK's), and B is applied as stored, not
+ *            through zhbmv's Hermitian completion of its upper triangle. */
+int lgpu_residuals(lgpu_ctx* ctx, int32_t nev, const double* omega_ri, const double* vr_ri, double* res);
+int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t maxiter, double tol,
+                           double* omega_ri, double* vr_ri, lgpu_stats* stats);
+
 /* Host utility: LAPACK zlarnv(idist=2) (uniform (-1,1) re and im), bit-exact port of
  * dlaruv's 48-bit multiplicative congruential generator; iseed[4] updated in place. */
 int lgpu_zlarnv(int32_t iseed[4], int32_t n, double* out_ri);

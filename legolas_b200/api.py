@@ -375,6 +375,28 @@ class Context:
             vr = np.array(vr, order="F")
         return omega, vr, _stats_dict(st)
 
+    def residuals(self, omega, vr) -> np.ndarray:
+        """get_residual for every pair (src/dataIO/mod_output.f08:511-545)."""
+        omega = np.ascontiguousarray(omega, dtype=np.complex128)
+        vr = np.asfortranarray(vr, dtype=np.complex128)
+        if vr.shape != (self.dim, len(omega)):
+            raise LegolasError(f"eigenvector array has shape {vr.shape}, expected {(self.dim, len(omega))}")
+        res = np.zeros(len(omega), dtype=np.float64)
+        self._check(self._lib.lgpu_residuals(self._h, len(omega), omega.ctypes.data, vr.ctypes.data,
+                                             res.ctypes.data_as(C.POINTER(C.c_double))), "residuals")
+        return res
+
+    def inverse_iteration(self, sigma: complex, maxiter: int = 0, tolerance: float = 5.0e-15,
+                          want_vector: bool = True):
+        """inverse_iteration (src/solvers/smod_inverse_iteration.f08:16-205): (omega, x, stats)."""
+        omega = np.zeros(1, dtype=np.complex128)
+        x = np.empty(self.dim, dtype=np.complex128) if want_vector else None
+        st = CStats()
+        self._check(self._lib.lgpu_inverse_iteration(self._h, sigma.real, sigma.imag, int(maxiter), float(tolerance),
+                                                     omega.ctypes.data, x.ctypes.data if want_vector else None,
+                                                     C.byref(st)), "inverse_iteration")
+        return complex(omega[0]), x, _stats_dict(st)
+
     def shift_invert_device(self, cfg: ArpackConfig, sigma: complex, resid_ptr: int, vr_ptr: int,
                             refine_steps: int = 0):
         ca = _arnoldi_c(cfg, sigma, refine_steps)
@@ -465,8 +487,20 @@ def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
     omega(nconv:) is NaN when ARPACK-style convergence was not reached for all nev (a warning,
     not an error, in the reference: mod_arpack_type.f08:375-381)."""
     sv = settings.solvers
+    if sv.solver == "inverse-iteration":
+        # mod_solvers.f08:92-123 dispatch; one eigenpair, omega(1) / vr(:, 1)
+        sigma = complex(sv.sigma)
+        if sigma != sigma:
+            raise LegolasError("sigma must be set for the inverse-iteration solver")
+        if sv.maxiter < 0:
+            raise LegolasError(f"maxiter has to be positive, but is equal to {sv.maxiter}")
+        if sigma == 0:
+            raise LegolasError("inverse-iteration: sigma can not be equal to zero")
+        omega, x, stats = matrices.ctx.inverse_iteration(sigma, sv.maxiter, sv.tolerance)
+        return np.array([omega]), x.reshape(-1, 1), None, stats
     if sv.solver != "arnoldi":
-        raise LegolasError(f"solver {sv.solver!r} stays on the Fortran host; only 'arnoldi' is built here")
+        raise LegolasError(f"solver {sv.solver!r} stays on the Fortran host; 'arnoldi' and "
+                           "'inverse-iteration' are built here")
     if sv.arpack_mode != "shift-invert":
         raise LegolasError(f"arpack_mode {sv.arpack_mode!r} stays on the Fortran host; "
                            "only 'shift-invert' is built here")

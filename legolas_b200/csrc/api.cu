@@ -776,6 +776,135 @@ int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refin
   });
 }
 
+namespace {
+
+// hwork[0..2] of the last vec_dot2 -> host (synchronises the stream)
+void fetch_dots(lgpu_ctx* c, cd out[3]) {
+  c->h_stage.ensure(4);
+  CUDA_CHECK(cudaMemcpyAsync(c->h_stage.p, c->khwork.p, 3 * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 3; ++k) out[k] = c->h_stage.p[k];
+}
+
+void dev_bx(lgpu_ctx* c, const cd* x, cd* y) {
+  if (c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
+    bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->bell_w, x, y, c->stream, &c->log);
+  else
+    block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, y, c->stream, &c->log);
+}
+
+}  // namespace
+
+int lgpu_residuals(lgpu_ctx* ctx, int32_t nev, const double* omega_ri, const double* vr_ri, double* res) {
+  return guarded(ctx, [&] {
+    if (!ctx->assembled()) return fail(ctx, LGPU_ESTATE, "residuals: matrices not assembled");
+    if (nev < 0 || (nev > 0 && (!omega_ri || !vr_ri || !res))) return fail(ctx, LGPU_EINVAL, "null argument");
+    ensure_vectors(ctx);
+    ensure_krylov_work(ctx);
+    ctx->log.stream = ctx->stream;
+    const KrylovWork kw = kwork(ctx);
+    const size_t bytes = sizeof(cd) * ctx->N;
+    for (int k = 0; k < nev; ++k) {
+      const cd om{omega_ri[2 * k], omega_ri[2 * k + 1]};
+      if (std::fabs(om.x) <= DP_LIMIT && std::fabs(om.y) <= DP_LIMIT) { res[k] = 0.0; continue; }   // is_zero
+      CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, vr_ri + 2 * static_cast<size_t>(k) * ctx->N, bytes,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+      // y = A v - omega B v
+      block_matvec(ctx->G, ctx->A.p, ctx->B.p, cd{1.0, 0.0}, cd{-om.x, -om.y}, ctx->vx.p, nullptr, ctx->vy.p,
+                   ctx->stream, &ctx->log);
+      cd d[3], e[3];
+      vec_dot2(ctx->N, ctx->vy.p, ctx->vy.p, ctx->vy.p, kw, ctx->stream, &ctx->log);
+      fetch_dots(ctx, d);
+      vec_dot2(ctx->N, ctx->vx.p, ctx->vx.p, ctx->vx.p, kw, ctx->stream, &ctx->log);
+      fetch_dots(ctx, e);
+      res[k] = std::sqrt(d[2].x) / (std::hypot(om.x, om.y) * std::sqrt(e[2].x));
+    }
+    return LGPU_OK;
+  });
+}
+
+int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t maxiter, double tol,
+                           double* omega_ri, double* vr_ri, lgpu_stats* stats) {
+  return guarded(ctx, [&] {
+    if (!ctx->assembled()) return fail(ctx, LGPU_ESTATE, "inverse_iteration: matrices not assembled");
+    if (!omega_ri) return fail(ctx, LGPU_EINVAL, "null argument");
+    if (maxiter == 0) maxiter = 100;                 // smod_inverse_iteration.f08:59-61
+    if (maxiter < 0) return fail(ctx, LGPU_EINVAL, "maxiter has to be positive");
+    if (sigma_re == 0.0 && sigma_im == 0.0) return fail(ctx, LGPU_EINVAL, "inverse-iteration: sigma can not be equal to zero");
+    int rc = do_factorize(ctx, cd{sigma_re, sigma_im});
+    if (rc != LGPU_OK) return rc;
+    ensure_krylov_work(ctx);
+    const KrylovWork kw = kwork(ctx);
+    lgpu_ctx* c = ctx;
+    const int n = c->N;
+    cd* x = c->vx.p;
+    cd* r = c->vr.p;
+    cd* sv = c->vy.p;
+    cd d[3];
+    auto normalise = [&](cd* v) {
+      vec_dot2(n, v, v, v, kw, c->stream, &c->log);
+      fetch_dots(c, d);
+      const double inv = 1.0 / std::sqrt(d[2].x);
+      vec_axpby(n, cd{inv, 0.0}, v, cd{0.0, 0.0}, v, c->stream, &c->log);
+    };
+    // start vector: (A - sigma B)^-1 1
+    {
+      std::vector<cd> ones(static_cast<size_t>(n), cd{1.0, 0.0});
+      CUDA_CHECK(cudaMemcpyAsync(x, ones.data(), sizeof(cd) * n, cudaMemcpyHostToDevice, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    slu_solve(c->splan, c->sdev(), x, x, c->stream, &c->log);
+    normalise(x);
+    int i = 0;
+    bool converged = false;
+    cd ev{sigma_re, sigma_im};
+    while (i <= maxiter && !converged) {
+      dev_bx(c, x, r);                                                                        // r = B x
+      block_matvec(c->G, c->A.p, c->B.p, cd{1.0, 0.0}, cd{0.0, 0.0}, x, nullptr, sv, c->stream, &c->log);   // s = A x
+      vec_dot2(n, x, sv, r, kw, c->stream, &c->log);
+      fetch_dots(c, d);
+      ev = d[0] * crecip(d[1]);                                                                // x^H s / x^H r
+      vec_axpby(n, cd{1.0, 0.0}, sv, cd{-ev.x, -ev.y}, r, c->stream, &c->log);                 // s -= ev r
+      vec_dot2(n, sv, sv, sv, kw, c->stream, &c->log);
+      cd e[3];
+      fetch_dots(c, e);
+      if (std::sqrt(e[2].x) < std::hypot(ev.x, ev.y) * tol) { converged = true; break; }
+      ++i;
+      slu_solve(c->splan, c->sdev(), r, x, c->stream, &c->log);                                // x = M^-1 r
+      normalise(x);
+    }
+    omega_ri[0] = ev.x;
+    omega_ri[1] = ev.y;
+    if (vr_ri) {
+      std::vector<cd> h(static_cast<size_t>(n));
+      CUDA_CHECK(cudaMemcpyAsync(h.data(), x, sizeof(cd) * n, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      // make the largest coefficient real (first maximum, as idamax)
+      size_t im = 0;
+      double best = -1.0;
+      for (size_t k = 0; k < h.size(); ++k) {
+        const double a = std::hypot(h[k].x, h[k].y);
+        if (a > best) { best = a; im = k; }
+      }
+      const cd ph{h[im].x / best, -h[im].y / best};
+      for (size_t k = 0; k < h.size(); ++k) {
+        const cd v = h[k] * ph;
+        vr_ri[2 * k] = v.x;
+        vr_ri[2 * k + 1] = v.y;
+      }
+    }
+    if (stats) {
+      *stats = lgpu_stats{};
+      stats->info = converged ? 0 : 1;
+      stats->nconv = converged ? 1 : 0;
+      stats->n_op = i;
+      stats->lu_info = c->lu_info;
+      stats->t_factor_ms = c->t_factor;
+    }
+    return LGPU_OK;
+  });
+}
+
 int lgpu_shift_invert(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_ri,
                       double* omega_ri, double* vr_ri, lgpu_stats* stats) {
   return guarded(ctx, [&] {

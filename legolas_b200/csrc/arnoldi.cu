@@ -545,6 +545,44 @@ vec_axpby_basis_kernel(BasisLayout L, cd a, cd* __restrict__ r, cd b, const cd* 
   if (i < L.n) r[i] = a * r[i] + b * V[basis_off(L, i, col)];
 }
 
+// out[0] = x^H s, out[1] = x^H r (zdotc), out[2] = (||x||^2, 0): CTA partials, the last CTA sums
+// them in a fixed order
+__global__ void __launch_bounds__(256)
+vec_dot2_kernel(int n, const cd* __restrict__ x, const cd* __restrict__ sv, const cd* __restrict__ rv,
+                cd* __restrict__ partial, cd* out, unsigned int* ticket) {
+  __shared__ cd red[3][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cd a0{0.0, 0.0}, a1{0.0, 0.0};
+  double nn = 0.0;
+  for (int i = blockIdx.x * 256 + tid; i < n; i += gridDim.x * 256) {
+    const cd xi = x[i];
+    cfmac(a0, xi, sv[i]);
+    cfmac(a1, xi, rv[i]);
+    nn += abs2(xi);
+  }
+  a0.x = warp_sum(a0.x); a0.y = warp_sum(a0.y);
+  a1.x = warp_sum(a1.x); a1.y = warp_sum(a1.y);
+  nn = warp_sum(nn);
+  if (lane == 0) { red[0][warp] = a0; red[1][warp] = a1; red[2][warp] = cd{nn, 0.0}; }
+  __syncthreads();
+  if (tid < 3) {
+    cd t{0.0, 0.0};
+    for (int w = 0; w < 8; ++w) t += red[tid][w];
+    partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + tid] = t;
+  }
+  if (last_block_done(ticket, tid < 3)) {
+    if (warp < 3) {
+      cd t{0.0, 0.0};
+      for (unsigned int b = lane; b < gridDim.x; b += 32) t += partial[static_cast<size_t>(b) * PSTRIDE + warp];
+      t.x = warp_sum(t.x);
+      t.y = warp_sum(t.y);
+      if (lane == 0) out[warp] = t;
+    }
+    __syncthreads();
+    if (tid == 0) *ticket = 0u;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 vec_axpby_kernel(int n, cd a, cd* __restrict__ r, cd b, const cd* __restrict__ v) {
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -702,6 +740,16 @@ void vec_axpby_basis(const BasisLayout& L, cd a, cd* r, cd b, const cd* V, int c
                      cudaStream_t stream, LaunchLog* log) {
   log->begin(LK_OTHER, 48.0 * L.n);
   vec_axpby_basis_kernel<<<(L.n + 255) / 256, 256, 0, stream>>>(L, a, r, b, V, col);
+  log->end();
+  log->launches += 1;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void vec_dot2(int n, const cd* x, const cd* sv, const cd* rv, const KrylovWork& work, cudaStream_t stream,
+              LaunchLog* log) {
+  log->begin(LK_OTHER, 48.0 * n);
+  const int grid = std::max(1, std::min(sm_count(), (n + 255) / 256));
+  vec_dot2_kernel<<<grid, 256, 0, stream>>>(n, x, sv, rv, work.partial, work.hwork, work.ticket);
   log->end();
   log->launches += 1;
   CUDA_CHECK(cudaGetLastError());

@@ -207,14 +207,18 @@ __device__ __forceinline__ cd shfl_cd(cd v, int src) {
 
 // Forward sweep of one merged pair (all consumer warps).
 //   s: the two stacked right-hand sides (64, shared) ; out: reduced right-hand side (32, shared)
-//   g = L11^-1 (P s)_1  is kept for the back substitution ; out = (P s)_2 - L21 g
+//   g = L11^-1 (P s)_1 is kept for the back substitution ; out = (P s)_2 - M2 (P s)_1 with
+//   M2 = L21 L11^-1 formed by the factorisation: both products start from (P s)_1, so the pair
+//   costs one exchange of partial sums instead of two dependent ones.
 //   part: 2 x NCW x 32 partial sums
 __device__ __forceinline__ void pair_forward(const Ring& rg, RingPos& pos, const cd* s, cd* out,
                                              cd* __restrict__ gout, cd* part, int warp, int lane) {
   const int c0 = warp * CW;
   const cd* g0 = ring_acquire(rg, pos);
   const uint8_t* perm = reinterpret_cast<const uint8_t*>(g0 + PR_PERM);
-  const cd v1 = s[perm[lane]], v2 = s[perm[SB + lane]];
+  // lanes 0..3 hold the entries of (P s)_1 that multiply this warp's columns
+  const cd v1 = s[perm[c0 + (lane & (CW - 1))]];
+  const cd v2 = s[perm[SB + lane]];
   const cd* L = g0 + PR_L11I;
   cd ga{0.0, 0.0}, gb{0.0, 0.0};
 #pragma unroll
@@ -222,33 +226,33 @@ __device__ __forceinline__ void pair_forward(const Ring& rg, RingPos& pos, const
     const int col = c0 + c;
     const cd ma = lane >= col ? L[tri_lo_off(col) + lane - col] : cd{0.0, 0.0};
     const cd mb = lane >= col + 1 ? L[tri_lo_off(col + 1) + lane - col - 1] : cd{0.0, 0.0};
-    cfma(ga, ma, shfl_cd(v1, col));
-    cfma(gb, mb, shfl_cd(v1, col + 1));
+    cfma(ga, ma, shfl_cd(v1, c));
+    cfma(gb, mb, shfl_cd(v1, c + 1));
   }
   ring_release(rg, pos, lane);
-  part[warp * SB + lane] = ga + gb;
-  consumer_sync();
-  cd g = part[lane], g2 = part[SB + lane];
-#pragma unroll
-  for (int w = 2; w < NCW; w += 2) { g += part[w * SB + lane]; g2 += part[(w + 1) * SB + lane]; }
-  g += g2;
   const cd* M = ring_acquire(rg, pos);
   cd aa{0.0, 0.0}, ab{0.0, 0.0};
 #pragma unroll
   for (int c = 0; c < CW; c += 2) {
-    cfma(aa, M[(c0 + c) * SB + lane], shfl_cd(g, c0 + c));
-    cfma(ab, M[(c0 + c + 1) * SB + lane], shfl_cd(g, c0 + c + 1));
+    cfma(aa, M[(c0 + c) * SB + lane], shfl_cd(v1, c));
+    cfma(ab, M[(c0 + c + 1) * SB + lane], shfl_cd(v1, c + 1));
   }
   ring_release(rg, pos, lane);
+  part[warp * SB + lane] = ga + gb;
   part[(NCW + warp) * SB + lane] = aa + ab;
   consumer_sync();
-  if (warp == 0) {
-    cd acc = part[NCW * SB + lane], acc2 = part[(NCW + 1) * SB + lane];
+  // warp w finishes rows 4w .. 4w+3: lanes 0-3 the reduced right-hand side, lanes 4-7 g
+  const cd v2row = shfl_cd(v2, c0 + (lane & (CW - 1)));
+  if (lane < 2 * CW) {
+    const int row = c0 + (lane & (CW - 1));
+    const cd* src = part + (lane < CW ? NCW * SB : 0) + row;
+    cd t0 = src[0], t1 = src[SB];
 #pragma unroll
-    for (int w = 2; w < NCW; w += 2) { acc += part[(NCW + w) * SB + lane]; acc2 += part[(NCW + w + 1) * SB + lane]; }
-    out[lane] = v2 - (acc + acc2);
-    gout[lane] = g;
+    for (int w = 2; w < NCW; w += 2) { t0 += src[w * SB]; t1 += src[(w + 1) * SB]; }
+    t0 += t1;
+    if (lane < CW) out[row] = v2row - t0; else gout[row] = t0;
   }
+  consumer_sync();
 }
 
 // Reduce the `cnt` rows of a chunk (first row r0 of level l0) to one row; returns the buffer
@@ -808,13 +812,30 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     }
   }
   __syncthreads();
+  // M2 = L21 L11^-1 over L21 (rows 32..63, columns 0..31 of W): thread (i, 4 columns)
+  {
+    const int i = tid & 31, cg = tid >> 5;
+    cd m2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = cg * 4 + q;
+      cd v{0.0, 0.0};
+      for (int k = c; k < SB; ++k) cfma(v, W[(32 + i) * WLD + k], X[k * 33 + c]);
+      m2[q] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) W[(32 + i) * WLD + cg * 4 + q] = m2[q];
+  }
+  __syncthreads();
   cd* rec = a.pairs + static_cast<size_t>(p) * PAIR_STRIDE;
   if (tid < 64) reinterpret_cast<uint8_t*>(rec + PR_PERM)[tid] = static_cast<uint8_t>(prm[tid]);
   for (int e = tid; e < SB2; e += blockDim.x) {
     const int i = e & 31, c = e >> 5;
     // scale of pivot row c folded into column c of L11^-1; reduced rows return to their own scale
     if (i >= c) rec[PR_L11I + tri_lo_off(c) + i - c] = X[i * 33 + c] * rscale[prm[c]];
-    rec[PR_L21 + e] = W[(32 + i) * WLD + c] * (1.0 / rscale[prm[32 + i]]);
+    // M2 acts on the scaled pivot rows (column c) and returns reduced rows to their own scale
+    rec[PR_L21 + e] = W[(32 + i) * WLD + c] * (rscale[prm[c]] / rscale[prm[32 + i]]);
     rec[PR_E + e] = W[i * WLD + 32 + c];
     rec[PR_F + e] = W[i * WLD + 64 + c];
     // U leaves with unit diagonal: row i divided by U_ii, whose reciprocal takes the diagonal slot

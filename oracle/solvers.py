@@ -174,3 +174,63 @@ def shift_invert_extended(A, B, sigma, nev, ncv=0, maxiter=0, tol=0.0, which="LM
     except ArpackNoConvergence as exc:
         nu, vr = exc.eigenvalues, exc.eigenvectors
     return sigma + 1.0 / nu, vr
+
+
+# --------------------------------------------------------------------------- rows N1 / N4
+def residuals(Ab, Bb, kl, ku, omega, vr):
+    """get_residual for every eigenpair (src/dataIO/mod_output.f08:511-545):
+    || A v - omega B v ||_2 / || omega v ||_2, and 0 where omega is zero by is_zero
+    (|Re| <= 5e-15 and |Im| <= 5e-15, src/mod_check_values.f08:143-161)."""
+    omega = np.asarray(omega, dtype=np.complex128)
+    out = np.zeros(len(omega))
+    for k, om in enumerate(omega):
+        if abs(om.real) <= 5.0e-15 and abs(om.imag) <= 5.0e-15:
+            continue
+        v = np.ascontiguousarray(vr[:, k])
+        y = banded_matvec(Ab, kl, ku, v) - om * banded_matvec(Bb, kl, ku, v)
+        out[k] = np.linalg.norm(y) / np.linalg.norm(om * v)
+    return out
+
+
+def inverse_iteration(Ab, Bb, kl, ku, sigma, maxiter=0, tol=5.0e-15, start="lapack"):
+    """inverse_iteration (src/solvers/smod_inverse_iteration.f08:16-205) on LAPACK band storage.
+
+    start = "lapack": x0 solves U x0 = 1 with the U of zgbtrf, as the reference (:117-119);
+    start = "solve":  x0 = (A - sigma B)^-1 1, the start vector of the device implementation (its
+    factors are not LAPACK's).  B is applied as stored; the reference goes through zhbmv on the
+    upper triangle, identical for the Hermitian B of every configuration without Hall terms.
+    Returns (omega, x with its largest entry made real, info dict)."""
+    from scipy.linalg import blas
+
+    if maxiter == 0:
+        maxiter = 100                       # :59-61
+    if maxiter < 0:
+        raise ValueError(f"maxiter has to be positive, but is equal to {maxiter}")
+    if sigma == 0:
+        raise ValueError("inverse-iteration: sigma can not be equal to zero")
+    n = Ab.shape[1]
+    lu = BandedLU(Ab - sigma * Bb, kl, ku)
+    ones = np.ones(n, dtype=np.complex128)
+    if start == "lapack":
+        # ztbsv('U','N','N', n, kl+ku, LU, ld, x): rows 0..kl+ku of the factored band are U
+        x = blas.ztbsv(kl + ku, np.asfortranarray(lu.lu[: kl + ku + 1]), ones, lower=0)
+    else:
+        x = lu.solve(ones)
+        x = x / np.linalg.norm(x)
+    i = 0
+    converged = False
+    ev = complex(sigma)
+    while i <= maxiter and not converged:
+        r = banded_matvec(Bb, kl, ku, x)
+        s = banded_matvec(Ab, kl, ku, x)
+        ev = np.vdot(x, s) / np.vdot(x, r)
+        s = s - ev * r
+        if np.linalg.norm(s) < abs(ev) * tol:
+            converged = True
+            break
+        i += 1
+        x = lu.solve(r)
+        x = x / np.linalg.norm(x)
+    im = int(np.argmax(np.abs(x)))          # idamax on abs(x): first maximum
+    x = x * (np.conj(x[im]) / abs(x[im]))
+    return complex(ev), x, {"iterations": i, "converged": converged}

@@ -239,3 +239,59 @@ def test_zlarnv_is_deterministic_and_uniform():
     assert np.array_equal(v, solvers.zlarnv(1000))
     assert np.all(np.abs(v.real) < 1) and np.all(np.abs(v.imag) < 1)
     assert abs(v.real.mean()) < 0.1
+
+
+# ----------------------------------------------------------------- rows N1 / N4 of the scope table
+def _small_pencil(name="adiabatic_homo", gridpts=12):
+    so, go, xgo, fo = eq.EQUILIBRIA[name](gridpts=gridpts)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    return A, B
+
+
+def test_inverse_iteration_converges_to_the_nearest_eigenvalue():
+    """smod_inverse_iteration.f08 restated: against the dense generalized eigenvalues (the
+    reference has no unit test or golden value for this solver: parity is anchored on its call
+    sequence)."""
+    import scipy.linalg as sla
+    A, B = _small_pencil()
+    w = sla.eigvals(A.to_dense(), B.to_dense())
+    w = w[np.isfinite(w)]
+    # a simple, well separated eigenvalue (the pencil also has a large null space)
+    cand = w[np.abs(w) > 0.5]
+    gaps = np.array([np.sort(np.abs(w - c))[1] for c in cand])
+    target = cand[np.argmax(gaps / np.abs(cand))]
+    sigma = target * (1.0 + 2e-3) + 1e-3j
+    for start in ("lapack", "solve"):
+        ev, x, info = solvers.inverse_iteration(A.to_band(), B.to_band(), 31, 31, sigma, maxiter=200, tol=1e-11,
+                                                 start=start)
+        assert info["converged"], (start, info)
+        assert abs(ev - target) <= 1e-8 * abs(target), (start, ev, target)
+        im = int(np.argmax(np.abs(x)))
+        assert abs(x[im].imag) <= 1e-14 * abs(x[im]) and x[im].real > 0     # largest entry made real
+        assert abs(np.linalg.norm(x) - 1.0) <= 1e-12
+        res = solvers.residuals(A.to_band(), B.to_band(), 31, 31, [ev], x.reshape(-1, 1))
+        assert res[0] <= 1e-9
+
+
+def test_inverse_iteration_default_tolerance_runs_to_maxiter():
+    """tolerance defaults to dp_LIMIT = 5e-15 (mod_solver_settings.f08:43): unreachable, the loop
+    stops after maxiter + 1 solves and the eigenvalue is still returned (a warning in the reference)."""
+    A, B = _small_pencil()
+    ev, x, info = solvers.inverse_iteration(A.to_band(), B.to_band(), 31, 31, 1.2 + 0.3j, maxiter=7)
+    assert not info["converged"] and info["iterations"] == 8
+    assert np.isfinite(ev)
+
+
+def test_residuals_zero_rule_and_scaling():
+    A, B = _small_pencil()
+    rng = np.random.default_rng(2)
+    n = A.n
+    vr = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    omega = np.array([0.7 - 0.1j, 3e-15 + 2e-15j, -1.3 + 0.0j])
+    res = solvers.residuals(A.to_band(), B.to_band(), 31, 31, omega, vr)
+    assert res[1] == 0.0                                        # is_zero(omega) -> 0
+    for k in (0, 2):
+        y = A.matvec(vr[:, k]) - omega[k] * B.matvec(vr[:, k])
+        assert abs(res[k] - np.linalg.norm(y) / (abs(omega[k]) * np.linalg.norm(vr[:, k]))) <= 1e-13 * res[k]
+    res2 = solvers.residuals(A.to_band(), B.to_band(), 31, 31, omega, 5.0 * vr)
+    assert np.allclose(res, res2, rtol=1e-13)                   # scale invariant
