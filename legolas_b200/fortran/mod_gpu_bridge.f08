@@ -78,12 +78,33 @@ module mod_gpu_bridge
       complex(c_double_complex), intent(out) :: vr(*)
       type(lgpu_stats), intent(out) :: stats
     end function lgpu_shift_invert
+
+    integer(c_int) function lgpu_inverse_iteration(ctx, sigma_re, sigma_im, maxiter, tol, omega, vr, stats) &
+      bind(C, name="lgpu_inverse_iteration")
+      import :: c_ptr, c_int, c_double, c_double_complex, lgpu_stats
+      type(c_ptr), value :: ctx
+      real(c_double), value :: sigma_re, sigma_im, tol
+      integer(c_int), value :: maxiter
+      complex(c_double_complex), intent(out) :: omega(*)
+      complex(c_double_complex), intent(out) :: vr(*)
+      type(lgpu_stats), intent(out) :: stats
+    end function lgpu_inverse_iteration
+
+    integer(c_int) function lgpu_residuals(ctx, nev, omega, vr, res) bind(C, name="lgpu_residuals")
+      import :: c_ptr, c_int, c_double, c_double_complex
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: nev
+      complex(c_double_complex), intent(in) :: omega(*)
+      complex(c_double_complex), intent(in) :: vr(*)
+      real(c_double), intent(out) :: res(*)
+    end function lgpu_residuals
   end interface
 
   !> one context per run: owns the device-resident A, B, factors and Krylov basis
   type(c_ptr), save :: gpu_ctx = c_null_ptr
 
   public :: build_matrices_gpu, solve_arpack_shift_invert_gpu, materialise_matrix_gpu
+  public :: inverse_iteration_gpu, residuals_gpu
 
 contains
 
@@ -244,6 +265,43 @@ contains
     call arpack_cfg%parse_zneupd_info()
     call arpack_cfg%parse_finished_stats()
   end subroutine solve_arpack_shift_invert_gpu
+
+
+  !> Drop-in for the body of inverse_iteration (src/solvers/smod_inverse_iteration.f08:16-205);
+  !! the argument checks of the reference stay in front of it.
+  subroutine inverse_iteration_gpu(settings, omega, vr)
+    use mod_settings, only: settings_t
+    use mod_logging, only: logger, str
+    type(settings_t), intent(in) :: settings
+    complex(dp), intent(out) :: omega(:)
+    complex(dp), intent(out) :: vr(:, :)
+    type(lgpu_stats) :: st
+    integer :: rc
+
+    rc = lgpu_inverse_iteration( &
+      gpu_ctx, real(settings%solvers%sigma), aimag(settings%solvers%sigma), &
+      settings%solvers%maxiter, settings%solvers%tolerance, omega, vr, st &
+    )
+    if (rc /= 0) then
+      call logger%error("legolas_b200: lgpu_inverse_iteration failed with " // str(rc))
+      return
+    end if
+    call logger%info("Iteration completed after " // str(st%n_op) // " iterations.")
+    if (st%info /= 0) call logger%warning("Inverse iteration failed to converge! (maxiter reached)")
+  end subroutine inverse_iteration_gpu
+
+
+  !> Drop-in for the loop of write_residual_data (src/dataIO/mod_output.f08:445-473).
+  subroutine residuals_gpu(eigenvalues, eigenvectors, residuals)
+    use mod_logging, only: logger, str
+    complex(dp), intent(in) :: eigenvalues(:)
+    complex(dp), intent(in) :: eigenvectors(:, :)
+    real(dp), intent(out) :: residuals(:)
+    integer :: rc
+
+    rc = lgpu_residuals(gpu_ctx, size(eigenvalues), eigenvalues, eigenvectors, residuals)
+    if (rc /= 0) call logger%error("legolas_b200: lgpu_residuals failed with " // str(rc))
+  end subroutine residuals_gpu
 
 
   !> Lazily rebuilds a matrix_t from the device matrix (only needed for write_matrices,
