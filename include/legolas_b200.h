@@ -173,6 +173,12 @@ void lgpu_host_free(void* ptr);
  *            LAPACK's U^-1 1 (the factors are not LAPACK's), and B is applied as stored, not
  *            through zhbmv's Hermitian completion of its upper triangle. */
 int lgpu_residuals(lgpu_ctx* ctx, int32_t nev, const double* omega_ri, const double* vr_ri, double* res);
+/* eigenfunctions: replaces base_ef_t%assemble (src/eigenfunctions/mod_base_efs.f08:35-61), i.e.
+ *            assemble_eigenfunction + retransform_eigenfunction (mod_ef_assembly.f08:16-106) for all 8
+ *            variables and the selected eigenvectors.  vr_ri: N x (max idx) complex host, ld = N;
+ *            idxs: nsel 1-based column indices (idxs_to_assemble); out_ri: complex
+ *            [8][nsel][2*gridpts-1], i.e. quantities(:, i) of variable p at ((p*nsel + i)*npts). */
+int lgpu_eigenfunctions(lgpu_ctx* ctx, const double* vr_ri, int32_t nsel, const int32_t* idxs, double* out_ri);
 int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t maxiter, double tol,
                            double* omega_ri, double* vr_ri, lgpu_stats* stats);
 

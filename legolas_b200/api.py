@@ -386,6 +386,20 @@ class Context:
                                              res.ctypes.data_as(C.POINTER(C.c_double))), "residuals")
         return res
 
+    def eigenfunctions(self, vr, idxs, state_vector=("rho", "v1", "v2", "v3", "T", "a1", "a2", "a3")) -> dict:
+        """base_ef_t%assemble for every variable (src/eigenfunctions/mod_base_efs.f08:35-61):
+        {name: (2 G - 1, len(idxs)) complex}; ``idxs`` are 1-based columns of ``vr`` (idxs_to_assemble)."""
+        vr = np.asfortranarray(vr, dtype=np.complex128)
+        idxs = np.ascontiguousarray(idxs, dtype=np.int32)
+        if vr.shape[0] != self.dim or (len(idxs) and (idxs.min() < 1 or idxs.max() > vr.shape[1])):
+            raise LegolasError("eigenfunctions: eigenvector array / indices do not match the matrices")
+        npts = 2 * (self.dim // 16) - 1
+        out = np.zeros((8, len(idxs), npts), dtype=np.complex128)
+        self._check(self._lib.lgpu_eigenfunctions(self._h, vr.ctypes.data, len(idxs),
+                                                  idxs.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data),
+                    "eigenfunctions")
+        return {name: out[p].T.copy(order="F") for p, name in enumerate(state_vector)}
+
     def inverse_iteration(self, sigma: complex, maxiter: int = 0, tolerance: float = 5.0e-15,
                           want_vector: bool = True):
         """inverse_iteration (src/solvers/smod_inverse_iteration.f08:16-205): (omega, x, stats)."""

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblegolas_b200.so")
-SOURCES = ["api.cu", "assemble.cu", "slu.cu", "arnoldi.cu", "bsparse.cu"]
-HEADERS = ["common.cuh", "assemble.cuh", "slu.cuh", "arnoldi.cuh", "bsparse.cuh", "iram.hpp", "dense_host.hpp",
+SOURCES = ["api.cu", "assemble.cu", "slu.cu", "arnoldi.cu", "bsparse.cu", "efs.cu"]
+HEADERS = ["common.cuh", "assemble.cuh", "slu.cuh", "arnoldi.cuh", "bsparse.cuh", "efs.cuh", "iram.hpp", "dense_host.hpp",
            "terms.def", os.path.join("..", "..", "include", "legolas_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -15,6 +15,7 @@
 #include "assemble.cuh"
 #include "slu.cuh"
 #include "bsparse.cuh"
+#include "efs.cuh"
 #include "common.cuh"
 #include "iram.hpp"
 
@@ -88,9 +89,13 @@ struct lgpu_ctx {
   SluPlan splan;
   DevBuf<cd> pairs, topfac, fwork, rhs, gvec, xpad;
   DevBuf<int32_t> d_info;
+  DevBuf<double> grid_copy;     // base grid of the last assembly (eigenfunction assembly)
+  DevBuf<cd> ef_in, ef_out;
+  DevBuf<int32_t> ef_idx;
   DevBuf<cd> bell_val;          // compressed copy of B for the operator application
   DevBuf<int32_t> bell_col, bell_width;
   int bell_w = -1;              // longest row of B; -1: not built for the current B
+  bool have_grid = false;       // grid_copy matches the resident matrices
   DevBuf<unsigned long long> d_sync;
   unsigned long long solve_epoch = 0;
   bool factorized = false;
@@ -249,6 +254,9 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
   c->t_assemble = ms;
   c->have[0] = c->have[1] = true;
   c->bell_w = -1;
+  c->grid_copy.ensure(G);
+  CUDA_CHECK(cudaMemcpyAsync(c->grid_copy.p, d_grid, sizeof(double) * G, cudaMemcpyDeviceToDevice, c->stream));
+  c->have_grid = true;
   return LGPU_OK;
 }
 
@@ -721,6 +729,7 @@ int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const 
     CUDA_CHECK(cudaMemcpy(ctx->masks.p, masks.data(), masks.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemset(ctx->natmasks.p, 0, (2 * 2 * 4 * 8 + 2) * sizeof(uint32_t)));
     ctx->have[which] = true;
+    ctx->have_grid = false;
     if (which == 1) ctx->bell_w = -1;
     return LGPU_OK;
   });
@@ -819,6 +828,34 @@ int lgpu_residuals(lgpu_ctx* ctx, int32_t nev, const double* omega_ri, const dou
       fetch_dots(ctx, e);
       res[k] = std::sqrt(d[2].x) / (std::hypot(om.x, om.y) * std::sqrt(e[2].x));
     }
+    return LGPU_OK;
+  });
+}
+
+int lgpu_eigenfunctions(lgpu_ctx* ctx, const double* vr_ri, int32_t nsel, const int32_t* idxs, double* out_ri) {
+  return guarded(ctx, [&] {
+    if (!ctx->assembled() || !ctx->have_grid)
+      return fail(ctx, LGPU_ESTATE, "eigenfunctions: needs matrices assembled by lgpu_assemble (grid, geometry)");
+    if (nsel < 0 || (nsel > 0 && (!vr_ri || !idxs || !out_ri))) return fail(ctx, LGPU_EINVAL, "null argument");
+    if (nsel == 0) return LGPU_OK;
+    const size_t n = static_cast<size_t>(ctx->N);
+    const int npts = 2 * ctx->G - 1;
+    ctx->ef_in.ensure(n * nsel);
+    ctx->ef_out.ensure(static_cast<size_t>(8) * npts * nsel);
+    ctx->ef_idx.ensure(nsel);
+    std::vector<int32_t> local(nsel);
+    for (int s = 0; s < nsel; ++s) {
+      if (idxs[s] < 1) return fail(ctx, LGPU_EINVAL, "eigenfunctions: indices are 1-based");
+      local[s] = s;   // the selected columns are packed on the way to the device
+      CUDA_CHECK(cudaMemcpyAsync(ctx->ef_in.p + n * s, vr_ri + 2 * n * static_cast<size_t>(idxs[s] - 1), sizeof(cd) * n,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(ctx->ef_idx.p, local.data(), sizeof(int32_t) * nsel, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->log.stream = ctx->stream;
+    assemble_eigenfunctions(ctx->G, ctx->settings.geometry, ctx->grid_copy.p, ctx->ef_in.p, n, nsel, ctx->ef_idx.p,
+                            ctx->ef_out.p, ctx->stream, &ctx->log);
+    CUDA_CHECK(cudaMemcpyAsync(out_ri, ctx->ef_out.p, sizeof(cd) * 8 * npts * nsel, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LGPU_OK;
   });
 }

@@ -90,6 +90,15 @@ module mod_gpu_bridge
       type(lgpu_stats), intent(out) :: stats
     end function lgpu_inverse_iteration
 
+    integer(c_int) function lgpu_eigenfunctions(ctx, vr, nsel, idxs, out) bind(C, name="lgpu_eigenfunctions")
+      import :: c_ptr, c_int, c_double_complex
+      type(c_ptr), value :: ctx
+      complex(c_double_complex), intent(in) :: vr(*)
+      integer(c_int), value :: nsel
+      integer(c_int), intent(in) :: idxs(*)
+      complex(c_double_complex), intent(out) :: out(*)
+    end function lgpu_eigenfunctions
+
     integer(c_int) function lgpu_residuals(ctx, nev, omega, vr, res) bind(C, name="lgpu_residuals")
       import :: c_ptr, c_int, c_double, c_double_complex
       type(c_ptr), value :: ctx
@@ -104,7 +113,7 @@ module mod_gpu_bridge
   type(c_ptr), save :: gpu_ctx = c_null_ptr
 
   public :: build_matrices_gpu, solve_arpack_shift_invert_gpu, materialise_matrix_gpu
-  public :: inverse_iteration_gpu, residuals_gpu
+  public :: inverse_iteration_gpu, residuals_gpu, base_eigenfunctions_gpu
 
 contains
 
@@ -289,6 +298,20 @@ contains
     call logger%info("Iteration completed after " // str(st%n_op) // " iterations.")
     if (st%info /= 0) call logger%warning("Inverse iteration failed to converge! (maxiter reached)")
   end subroutine inverse_iteration_gpu
+
+
+  !> Drop-in for the loop over base_efs(i)%assemble in eigenfunctions_t%assemble: quantities(:, :, p)
+  !! is base_efs(p)%quantities for the p-th state-vector entry.
+  subroutine base_eigenfunctions_gpu(idxs_to_assemble, right_eigenvectors, quantities)
+    use mod_logging, only: logger, str
+    integer, intent(in) :: idxs_to_assemble(:)
+    complex(dp), intent(in) :: right_eigenvectors(:, :)
+    complex(dp), intent(out) :: quantities(:, :, :)   ! (ef_gridpts, size(idxs), 8)
+    integer :: rc
+
+    rc = lgpu_eigenfunctions(gpu_ctx, right_eigenvectors, size(idxs_to_assemble), idxs_to_assemble, quantities)
+    if (rc /= 0) call logger%error("legolas_b200: lgpu_eigenfunctions failed with " // str(rc))
+  end subroutine base_eigenfunctions_gpu
 
 
   !> Drop-in for the loop of write_residual_data (src/dataIO/mod_output.f08:445-473).

@@ -195,13 +195,22 @@ def _read_blocks(st, data, vt, str_len_arr):
             nb_ef_names = st.i()
             st.strs(str_len_arr, nb_ef_names)
             ef_gridsize = data["ef_gridpoints"]
-        st.arr("f8", ef_gridsize)
+        data["ef_grid"] = st.arr("f8", ef_gridsize)
         if vt >= (1, 1, 4):
             flags = st.arr("i4", st.i())
             idxs = st.arr("i4", st.i())
             nb_written = len(idxs)
+            data["ef_written_idxs"] = idxs          # 1-based eigenvalue indices (mod_output.f08:410-411)
             del flags
-        st.pos += 16 * data["ef_gridpoints"] * nb_written * nb_ef_names
+        # one (ef_gridpts, nb_written) column-major block per state-vector entry (mod_output.f08:412-414)
+        if vt >= (2, 0, 0):
+            npts = data["ef_gridpoints"]
+            data["eigenfunctions"] = {
+                name: st.arr("c16", npts * nb_written).reshape((npts, nb_written), order="F")
+                for name in data["state_vector"]
+            }
+        else:
+            st.pos += 16 * data["ef_gridpoints"] * nb_written * nb_ef_names
     if data.get("has_derived_efs"):
         if vt >= (2, 0, 0):
             nb_names, size_names = st.take("ii")

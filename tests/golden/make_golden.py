@@ -6,6 +6,7 @@ the GPU box):  ``python tests/golden/make_golden.py``
 Sources (reference-owned data, never code):
   tests/regression_tests/baseline/BASE_*.dat      (Legolas 1.2.1 regression baselines)
   tests/pylbo_tests/utility_files/v2.0.0_mri_matrix.dat   (the only stored assembled A, B)
+  tests/pylbo_tests/utility_files/v2.0.0_mri_subset_efs.dat (eigenvectors + eigenfunctions + residuals)
 Each fixture keeps: eigenvalues, base grid, Gaussian grid, the stored equilibrium
 arrays, parameters, units and (for the MRI file) the matrix triplets and the Gauss
 nodes/weights printed in its header.
@@ -32,6 +33,8 @@ FILES = {
     "kh_cd_SI": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_SI_k2_-1_k3_pi.dat",
     "kh_cd_QR": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_QR_k2_-1_k3_pi.dat",
     "mri_matrix": "pylbo_tests/utility_files/v2.0.0_mri_matrix.dat",
+    # the only stored run with eigenvectors, eigenfunctions AND residuals (rows N1 of the scope table)
+    "mri_subset_efs": "pylbo_tests/utility_files/v2.0.0_mri_subset_efs.dat",
 }
 
 
@@ -53,6 +56,16 @@ def main():
         if "gauss_nodes" in d:
             out["gauss_nodes"] = d["gauss_nodes"]
             out["gauss_weights"] = d["gauss_weights"]
+        if "eigenfunctions" in d:
+            out["ef_grid"] = d["ef_grid"]
+            out["ef_written_idxs"] = d["ef_written_idxs"]
+            for name, arr in d["eigenfunctions"].items():
+                out["ef_" + name] = arr
+            out["state_vector"] = np.array(d["state_vector"])
+        if "eigenvectors" in d:
+            out["eigenvectors"] = d["eigenvectors"]
+        if "residuals" in d:
+            out["residuals"] = d["residuals"]
         if "matrix_A" in d:
             out["A_rows"], out["A_cols"], out["A_vals"] = d["matrix_A"]
             out["B_rows"], out["B_cols"], out["B_vals"] = d["matrix_B"]

@@ -102,3 +102,69 @@ def test_inverse_iteration_argument_checks(ctx):
     # default tolerance (5e-15) is unreachable: maxiter + 1 solves, eigenvalue still returned
     omega, x, stats = ctx.inverse_iteration(1.1 + 0.2j, maxiter=5)
     assert stats["info"] == 1 and stats["n_op"] == 6 and np.isfinite(omega)
+
+
+# ------------------------------------------------------------------ N1: eigenfunction assembly
+def test_eigenfunctions_replay_reference_stored_run(ctx, golden):
+    """The reference's own stored run (v2.0.0_mri_subset_efs.dat): its eigenvectors through the
+    device assembly give the eigenfunctions it wrote."""
+    g = golden("mri_subset_efs")
+    s, grid, fields = heq.mri_accretion(10)
+    assert np.allclose(grid.base_grid, g["grid"], rtol=0, atol=1e-14)
+    ctx.assemble(s, grid.base_grid, grid.gaussian_grid, fields)
+    efs = ctx.eigenfunctions(g["eigenvectors"], g["ef_written_idxs"])
+    for name in (str(x) for x in g["state_vector"]):
+        ref = g["ef_" + name]
+        assert efs[name].shape == ref.shape
+        assert np.all(np.abs(efs[name] - ref) <= 1e-12 * np.abs(ref).max()), name
+
+
+@pytest.mark.parametrize("name,gridpts", [("resistive_tearing", 51), ("magnetothermal_instabilities", 1001),
+                                          ("adiabatic_homo", 2)])
+def test_eigenfunctions_match_oracle(ctx, name, gridpts):
+    from oracle import eigenfunctions as oef
+    s, grid, fields = heq.EQUILIBRIA[name](gridpts)
+    ctx.assemble(s, grid.base_grid, grid.gaussian_grid, fields)
+    rng = np.random.default_rng(9)
+    n = 16 * gridpts
+    vr = np.asfortranarray(rng.standard_normal((n, 5)) + 1j * rng.standard_normal((n, 5)))
+    idxs = np.array([4, 1, 5], dtype=np.int32)          # 1-based, unordered subset
+    got = ctx.eigenfunctions(vr, idxs)
+    ref = oef.base_eigenfunctions(s.geometry, asm.STATE_VECTORS["mhd"], grid.base_grid, vr, idxs - 1)
+    for var in asm.STATE_VECTORS["mhd"]:
+        assert got[var].shape == (2 * gridpts - 1, 3)
+        assert np.all(np.abs(got[var] - ref[var]) <= 1e-12 * np.abs(ref[var]).max()), var
+
+
+def test_eigenfunctions_of_ritz_vectors_within_parity_bar(ctx):
+    """Eigenfunctions of the device Ritz vectors vs those of the oracle's, phase-normalised: the 1e-6
+    bar of the path."""
+    from oracle import eigenfunctions as oef
+    name, gridpts, sigma = "resistive_tearing", 201, 0.3 - 0.2j
+    s, grid, fields = heq.EQUILIBRIA[name](gridpts)
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert", number_of_eigenvalues=4, sigma=sigma)
+    so, go, xgo, fo = oeq.EQUILIBRIA[name](gridpts=gridpts)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    om_o, vr_o = osolvers.shift_invert(A.to_band(), B.to_band(), 31, 31, sigma, 4)
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    omega, vr, _, stats = lb.solve_evp(mats, s)
+    assert stats["nconv"] == 4
+    got = ctx.eigenfunctions(vr, np.arange(1, 5, dtype=np.int32))
+    for k in range(4):
+        j = int(np.argmin(np.abs(om_o - omega[k])))
+        assert abs(om_o[j] - omega[k]) <= 1e-8 * abs(omega[k])
+        ip = np.vdot(vr_o[:, j], vr[:, k])
+        phase = np.conj(ip) / abs(ip)
+        ref = oef.base_eigenfunctions(s.geometry, asm.STATE_VECTORS["mhd"], grid.base_grid, vr_o, [j])
+        for var in asm.STATE_VECTORS["mhd"]:
+            scale = max(np.abs(ref[var]).max(), 1e-300)
+            assert np.abs(got[var][:, k] * phase - ref[var][:, 0]).max() <= 1e-6 * max(scale, np.abs(ref["v1"]).max()), var
+
+
+def test_eigenfunctions_need_an_assembled_grid(ctx):
+    s, grid, fields = heq.EQUILIBRIA["adiabatic_homo"](11)
+    ctx.assemble(s, grid.base_grid, grid.gaussian_grid, fields)
+    r, c, v = ctx.export_coo("B")
+    ctx.import_coo("B", 176, r, c, v)                    # imported matrices carry no grid
+    with pytest.raises(lb.LgpuError):
+        ctx.eigenfunctions(np.zeros((176, 1), dtype=np.complex128), np.array([1], dtype=np.int32))
