@@ -166,6 +166,48 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def time_next_rows(lb, heq, ctx, s, grid, fields, sigma):
+    """Rows N1 / N4 of the scope table at the headline size, through the host API (host buffers in
+    and out, wall clock), next to the oracle on a bounded sample (seconds extrapolated linearly)."""
+    from oracle import assembly as asm
+    from oracle import eigenfunctions as oef
+    from oracle import equilibria as oeq
+    from oracle import solvers as osolvers
+
+    out = {}
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    omega, vr, _, _ = lb.solve_evp(mats, s)
+    idxs = np.arange(1, NEV + 1, dtype=np.int32)
+    for name, fn in (("eigenfunctions", lambda: ctx.eigenfunctions(vr, idxs)),
+                     ("residuals", lambda: ctx.residuals(omega, vr))):
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        out[name] = {"gpu_s": time.perf_counter() - t0, "pairs": NEV}
+    t0 = time.perf_counter()
+    oef.base_eigenfunctions(s.geometry, asm.STATE_VECTORS["mhd"], grid.base_grid, vr, [0])
+    out["eigenfunctions"]["cpu_s"] = (time.perf_counter() - t0) * NEV
+    out["eigenfunctions"]["cpu_sample"] = "oracle (Python loops) on 1 of 20 vectors, x20"
+    so, go, xgo, fo = oeq.magnetothermal_eq(gridpts=GRIDPTS)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    Ab, Bb = A.to_band(), B.to_band()
+    t0 = time.perf_counter()
+    osolvers.residuals(Ab, Bb, 31, 31, omega[:4], vr[:, :4])
+    out["residuals"]["cpu_s"] = (time.perf_counter() - t0) * NEV / 4
+    out["residuals"]["cpu_sample"] = "zgbmv-based oracle on 4 of 20 pairs, x5"
+    sig = complex(sigma) + (0.01 + 0.02j)   # away from the dense thermal sequence: a few tens of solves
+    ctx.inverse_iteration(sig, maxiter=30, tolerance=1e-12)
+    t0 = time.perf_counter()
+    ev, x, st = ctx.inverse_iteration(sig, maxiter=30, tolerance=1e-12)
+    out["inverse_iteration"] = {"gpu_s": time.perf_counter() - t0, "solves": st["n_op"], "converged": st["info"] == 0}
+    t0 = time.perf_counter()
+    ev_o, x_o, info = osolvers.inverse_iteration(Ab, Bb, 31, 31, sig, maxiter=30, tol=1e-12, start="solve")
+    out["inverse_iteration"]["cpu_s"] = time.perf_counter() - t0
+    out["inverse_iteration"]["cpu_solves"] = info["iterations"]
+    out["inverse_iteration"]["omega_rel_diff"] = abs(ev - ev_o) / abs(ev_o)
+    return out
+
+
 # ------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -336,6 +378,8 @@ def run_gpu(args):
             "phases_ms": ctx.phase_times(),
             "ranks": gathered,
         }
+        if world == 1 and not args.no_cpu_baseline:
+            line["next_rows"] = time_next_rows(lb, heq, ctx, s, grid, fields, sigma)
         if cpu is not None:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": os.cpu_count() or 1,
                                     "kind": "port", "sample": cpu["sample"],
