@@ -713,7 +713,6 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
   cd* X = W + 64 * WLD;                             // [32][33] inverse of L11
   cd* lcol = X + SB * 33;                           // [64]
   int* prm = reinterpret_cast<int*>(lcol + 64);     // [64]
-  __shared__ int piv_row;
   __shared__ double rscale[64];
   const int tid = threadIdx.x;
   const int p = blockIdx.x;
@@ -752,6 +751,10 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     W[i * WLD + c] = W[i * WLD + c] * rscale[i];
   }
   __syncthreads();
+  // 32 elimination steps.  Warp 0 does the sequential part of a step on its own (pivot search,
+  // row swap, multipliers: warp-synchronous, no CTA barrier), then all 8 warps apply the rank-1
+  // update: thread = (column c mod 32, row group), no index arithmetic in the loop.
+  const int lane = tid & 31, rg = tid >> 5;
   for (int k = 0; k < SB; ++k) {
     if (tid < 32) {
       // partial pivoting over rows k .. 63 of column k (two candidates per lane)
@@ -766,36 +769,47 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
         const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
         if (ob > b0 || (ob == b0 && oi < bi)) { b0 = ob; bi = oi; }
       }
-      if (tid == 0) {
-        piv_row = bi;
-        if (!(b0 > 0.0)) {   // exactly singular panel column: report like zgbtrf info > 0
-          const long long node = (static_cast<long long>(2 * p + 1) << a.level);
-          atomicCAS(a.info, 0, static_cast<int>(min(2 * node + 1, static_cast<long long>(a.n))));
-          W[bi * WLD + k] = cd{2.2250738585072014e-308, 0.0};
+      const int pr = bi;   // the butterfly leaves the same (value, index) in every lane
+      if (tid == 0 && !(b0 > 0.0)) {   // exactly singular panel column: report like zgbtrf info > 0
+        const long long node = (static_cast<long long>(2 * p + 1) << a.level);
+        atomicCAS(a.info, 0, static_cast<int>(min(2 * node + 1, static_cast<long long>(a.n))));
+        W[pr * WLD + k] = cd{2.2250738585072014e-308, 0.0};
+      }
+      __syncwarp();
+      if (pr != k) {
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const int c = lane + 32 * cc;
+          const cd t0 = W[k * WLD + c];
+          W[k * WLD + c] = W[pr * WLD + c];
+          W[pr * WLD + c] = t0;
+        }
+        if (lane == 0) { const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0; }
+      }
+      __syncwarp();
+      const cd pinv = crecip(W[k * WLD + k]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i > k) {
+          const cd l = W[i * WLD + k] * pinv;
+          lcol[i] = l;
+          W[i * WLD + k] = l;   // multiplier kept in place
         }
       }
     }
     __syncthreads();
-    const int pr = piv_row;
-    if (pr != k) {
-      if (tid < 96) {
-        const cd t0 = W[k * WLD + tid];
-        W[k * WLD + tid] = W[pr * WLD + tid];
-        W[pr * WLD + tid] = t0;
-      } else if (tid == 96) {
-        const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const int c = lane + 32 * cc;
+      if (c > k) {
+        const cd wk = W[k * WLD + c];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = rg + 8 * r;
+          if (i > k) cfms(W[i * WLD + c], lcol[i], wk);
+        }
       }
-    }
-    __syncthreads();
-    if (tid > k && tid < 64) {
-      const cd l = W[tid * WLD + k] * crecip(W[k * WLD + k]);
-      lcol[tid] = l;
-      W[tid * WLD + k] = l;   // multiplier kept in place
-    }
-    __syncthreads();
-    for (int e = tid; e < 64 * 96; e += blockDim.x) {
-      const int i = e / 96, c = e - i * 96;
-      if (i > k && c > k) cfms(W[i * WLD + c], lcol[i], W[k * WLD + c]);
     }
     __syncthreads();
   }
