@@ -710,8 +710,10 @@ constexpr int WLD = 97;   // padded row length of the 64 x 96 working matrix
 __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* W = reinterpret_cast<cd*>(smem_raw);          // [64][WLD]
-  cd* X = W + 64 * WLD;                             // [32][33] inverse of L11
-  cd* lcol = X + SB * 33;                           // [64]
+  cd* lcol = W + 64 * WLD;                          // [64]
+  // inverse of L11: lives in rows 32..63, columns 32..63 of W once the reduced rows stored there
+  // have been written out (keeps the CTA at 100 KB of shared memory: two CTAs per SM)
+  cd* X = W + 32 * WLD + 32;                        // X(i, c) at X[i * WLD + c]
   int* prm = reinterpret_cast<int*>(lcol + 64);     // [64]
   __shared__ double rscale[64];
   const int tid = threadIdx.x;
@@ -813,16 +815,28 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     }
     __syncthreads();
   }
-  // X = L11^-1 (unit lower triangular), one column per thread
+  // the reduced rows leave first ...
+  {
+    cd* Sn = a.dst + static_cast<size_t>(p) * ROW_STRIDE;
+    cd* Tn = Sn + SB2;
+    for (int e = tid; e < SB2; e += blockDim.x) {
+      const int i = e & 31, c = e >> 5;
+      const double unscale = 1.0 / rscale[prm[32 + i]];
+      Sn[e] = W[(32 + i) * WLD + 32 + c] * unscale;
+      Tn[e] = W[(32 + i) * WLD + 64 + c] * unscale;
+    }
+  }
+  __syncthreads();
+  // ... and their place takes X = L11^-1 (unit lower triangular), one column per thread
   if (tid < SB) {
     const int c = tid;
     for (int i = 0; i < SB; ++i) {
       cd v{i == c ? 1.0 : 0.0, 0.0};
       if (i > c) {
         v = cd{0.0, 0.0};
-        for (int j = c; j < i; ++j) cfms(v, W[i * WLD + j], X[j * 33 + c]);
+        for (int j = c; j < i; ++j) cfms(v, W[i * WLD + j], X[j * WLD + c]);
       }
-      X[i * 33 + c] = (i >= c) ? v : cd{0.0, 0.0};
+      X[i * WLD + c] = (i >= c) ? v : cd{0.0, 0.0};
     }
   }
   __syncthreads();
@@ -834,7 +848,7 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     for (int q = 0; q < 4; ++q) {
       const int c = cg * 4 + q;
       cd v{0.0, 0.0};
-      for (int k = c; k < SB; ++k) cfma(v, W[(32 + i) * WLD + k], X[k * 33 + c]);
+      for (int k = c; k < SB; ++k) cfma(v, W[(32 + i) * WLD + k], X[k * WLD + c]);
       m2[q] = v;
     }
     __syncthreads();
@@ -847,7 +861,7 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
   for (int e = tid; e < SB2; e += blockDim.x) {
     const int i = e & 31, c = e >> 5;
     // scale of pivot row c folded into column c of L11^-1; reduced rows return to their own scale
-    if (i >= c) rec[PR_L11I + tri_lo_off(c) + i - c] = X[i * 33 + c] * rscale[prm[c]];
+    if (i >= c) rec[PR_L11I + tri_lo_off(c) + i - c] = X[i * WLD + c] * rscale[prm[c]];
     // M2 acts on the scaled pivot rows (column c) and returns reduced rows to their own scale
     rec[PR_L21 + e] = W[(32 + i) * WLD + c] * (rscale[prm[c]] / rscale[prm[32 + i]]);
     rec[PR_E + e] = W[i * WLD + 32 + c];
@@ -857,14 +871,6 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
       const cd dinv = crecip(W[i * WLD + i]);
       rec[PR_U + tri_up_off(c) + i] = (i == c) ? dinv : W[i * WLD + c] * dinv;
     }
-  }
-  cd* Sn = a.dst + static_cast<size_t>(p) * ROW_STRIDE;
-  cd* Tn = Sn + SB2;
-  for (int e = tid; e < SB2; e += blockDim.x) {
-    const int i = e & 31, c = e >> 5;
-    const double unscale = 1.0 / rscale[prm[32 + i]];
-    Sn[e] = W[(32 + i) * WLD + 32 + c] * unscale;
-    Tn[e] = W[(32 + i) * WLD + 64 + c] * unscale;
   }
 }
 
@@ -1086,7 +1092,7 @@ RingShape bwd_shape(const StageArgs& a, bool top) {
   return RingShape{ns, nu, bytes(ns, nu)};
 }
 
-constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + SB * 33 + 64) + sizeof(int) * 64;
+constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + 64) + sizeof(int) * 64;   // 100.6 KB: two CTAs per SM
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
