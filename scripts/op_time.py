@@ -17,4 +17,4 @@ p = ctx.profile()
 ops = ("matvec", "fwd_stage0", "fwd_stage", "top_stage", "bwd_stage", "bwd_stage0")
 tot = sum(p[k][0] for k in ops) / max(p["matvec"][1], 1) * 1e3
 print("env", {k: v for k, v in os.environ.items() if k.startswith("LGPU_")}, "us/op %.1f" % tot,
-      " ".join(f"{k}={1e3*p[k][0]/max(p[k][1],1):.1f}" for k in ops + ("dots", "update", "scale")))
+      " ".join(f"{k}={1e3*p[k][0]/max(p[k][1],1):.1f}" for k in ops + ("cgs2_step", "dots", "update", "scale")))
