@@ -154,6 +154,17 @@ int lgpu_shift_invert(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resi
 int lgpu_shift_invert_device(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_dev,
                              double* omega_ri_host, double* vr_dev, lgpu_stats* stats);
 
+/* ---- row N3 of the scope table: ARPACK "general" mode ---------------------------------------
+ * Replaces solve_arpack_general (src/solvers/arnoldi/smod_arpack_general.f08:14-131), reached from
+ * solve_evp with solver = "arnoldi", arpack_mode = "general" (smod_arpack_main.f08:57-65: mode = 1,
+ * bmat = "I"): the standard problem OP x = omega x with OP = B^-1 A.  The reference re-factorises B
+ * on every operator application (zgbsv, src/solvers/mod_linear_systems.f08:33-62); here B is
+ * factorised once per call.  Same arguments and outputs as lgpu_shift_invert; cfg->sigma_* are
+ * ignored and omega are ARPACK's Ritz values themselves (no back-transformation).  The resident
+ * factorisation is dropped afterwards (lgpu_solve / lgpu_apply_op need a new lgpu_factorize). */
+int lgpu_arnoldi_general(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_ri,
+                         double* omega_ri, double* vr_ri, lgpu_stats* stats);
+
 /* Page-locked host memory for callers that want the eigenvector read-back (N x nev complex,
  * 51 MB at the headline size) at full PCIe speed instead of the pageable-memory staging path.
  * Any host pointer is accepted by every entry point; these are optional. */

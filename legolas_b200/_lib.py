@@ -79,6 +79,7 @@ SIGNATURES = {
     "lgpu_apply_op": (C.c_int, [_P, _P, _P, C.c_int32]),
     "lgpu_shift_invert": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),
     "lgpu_shift_invert_device": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),
+    "lgpu_arnoldi_general": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),
     "lgpu_residuals": (C.c_int, [_P, C.c_int32, _P, _P, _DP]),
     "lgpu_eigenfunctions": (C.c_int, [_P, _P, C.c_int32, _IP, _P]),
     "lgpu_inverse_iteration": (C.c_int, [_P, C.c_double, C.c_double, C.c_int32, C.c_double, _P, _P,

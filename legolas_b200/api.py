@@ -349,8 +349,13 @@ class Context:
         return y
 
     # ---- the eigen-solve
+    def arnoldi_general(self, cfg: ArpackConfig, refine_steps: int = 0, want_vectors: bool = True):
+        """solve_arpack_general (src/solvers/arnoldi/smod_arpack_general.f08:14-131): ARPACK on
+        OP = B^-1 A (mode 1, bmat "I"); returns (omega, vr, stats) like ``shift_invert``."""
+        return self.shift_invert(cfg, 0j, refine_steps, want_vectors, _entry="lgpu_arnoldi_general")
+
     def shift_invert(self, cfg: ArpackConfig, sigma: complex, refine_steps: int = 0,
-                     want_vectors: bool = True, vr_view: bool = False):
+                     want_vectors: bool = True, vr_view: bool = False, _entry: str = "lgpu_shift_invert"):
         """``vr_view=True`` returns the Ritz vectors as a view of the context's page-locked
         read-back buffer (valid until the next solve on this context) instead of a copy."""
         ca = _arnoldi_c(cfg, sigma, refine_steps)
@@ -368,9 +373,9 @@ class Context:
                 vr_view = True
                 vr = np.empty((cfg.evpdim, cfg.nev), dtype=np.complex128, order="F")
         st = CStats()
-        self._check(self._lib.lgpu_shift_invert(
+        self._check(getattr(self._lib, _entry)(
             self._h, C.byref(ca), resid.ctypes.data, omega.ctypes.data,
-            vr.ctypes.data if vr is not None else None, C.byref(st)), "shift_invert")
+            vr.ctypes.data if vr is not None else None, C.byref(st)), _entry[5:])
         if vr is not None and not vr_view:
             vr = np.array(vr, order="F")
         return omega, vr, _stats_dict(st)
@@ -497,7 +502,7 @@ def build_matrices(settings: Settings, grid: np.ndarray, gauss_grid: np.ndarray,
 
 def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
     """``call solve_evp(matrix_A, matrix_B, settings, omega, right_eigenvectors)`` for
-    ``solver = "arnoldi"``, ``arpack_mode = "shift-invert"``.  Returns (omega, vr, arpack_cfg, stats);
+    ``solver = "arnoldi"``, ``arpack_mode = "shift-invert"`` or ``"general"``.  Returns (omega, vr, arpack_cfg, stats);
     omega(nconv:) is NaN when ARPACK-style convergence was not reached for all nev (a warning,
     not an error, in the reference: mod_arpack_type.f08:375-381)."""
     sv = settings.solvers
@@ -515,9 +520,16 @@ def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
     if sv.solver != "arnoldi":
         raise LegolasError(f"solver {sv.solver!r} stays on the Fortran host; 'arnoldi' and "
                            "'inverse-iteration' are built here")
+    if sv.arpack_mode == "general":
+        # smod_arpack_main.f08:57-65: mode = 1, bmat = "I"; OP = B^-1 A
+        cfg = new_arpack_config(matrices.ctx.dim, mode=1, bmat="I", solver_settings=sv)
+        omega, vr, stats = matrices.ctx.arnoldi_general(cfg, sv.refine_steps)
+        cfg.info = stats["info"]
+        cfg.iparam.update({5: stats["nconv"], 9: stats["n_op"], 10: stats["n_bx"], 11: stats["n_reorth"]})
+        return omega, vr, cfg, stats
     if sv.arpack_mode != "shift-invert":
-        raise LegolasError(f"arpack_mode {sv.arpack_mode!r} stays on the Fortran host; "
-                           "only 'shift-invert' is built here")
+        # smod_arpack_main.f08:78-82
+        raise LegolasError(f"unknown mode for ARPACK: {sv.arpack_mode}")
     if math.isnan(sv.sigma.real) or math.isnan(sv.sigma.imag):
         raise LegolasError("sigma is not set")
     cfg = new_arpack_config(matrices.ctx.dim, mode=2, bmat="I", solver_settings=sv)

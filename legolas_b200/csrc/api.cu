@@ -99,6 +99,7 @@ struct lgpu_ctx {
   DevBuf<unsigned long long> d_sync;
   unsigned long long solve_epoch = 0;
   bool factorized = false;
+  bool factor_of_B = false;     // general mode: the resident factors are those of B, not of A - sigma B
   cd sigma{0.0, 0.0};
   int lu_info = 0;
 
@@ -120,7 +121,7 @@ struct lgpu_ctx {
   bool assembled() const { return have[0] && have[1]; }
   SluDevice sdev() {
     SluDevice d{};
-    d.A = A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
+    d.A = factor_of_B ? B.p : A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
     d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
     d.sync = d_sync.p; d.epoch = &solve_epoch;
     return d;
@@ -260,8 +261,11 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
   return LGPU_OK;
 }
 
-int do_factorize(lgpu_ctx* c, cd sigma) {
+// factors of A - sigma B, or (of_B, general mode: sigma ignored) of B itself
+int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
   if (!c->assembled()) return fail(c, LGPU_ESTATE, "factorize: matrices not assembled");
+  c->factor_of_B = of_B;
+  if (of_B) sigma = cd{0.0, 0.0};
   if (c->splan.n != c->G) {
     c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 3),
                              env_int("LGPU_SLU_TOP", 32));
@@ -313,15 +317,22 @@ void dev_solve(lgpu_ctx* c, const cd* b, cd* x, int refine) {
   slu_solve(c->splan, c->sdev(), rhs, x, c->stream, &c->log);
   for (int it = 0; it < refine; ++it) {
     // e = M^-1 (b - (A - sigma B) x) ; x += e
-    block_matvec(c->G, c->A.p, c->B.p, cd{-1.0, 0.0}, c->sigma, x, rhs, c->ve.p, c->stream,
-                 &c->log);
+    block_matvec(c->G, c->A.p, c->B.p, c->factor_of_B ? cd{0.0, 0.0} : cd{-1.0, 0.0},
+                 c->factor_of_B ? cd{-1.0, 0.0} : c->sigma, x, rhs, c->ve.p, c->stream, &c->log);
     slu_solve(c->splan, c->sdev(), c->ve.p, c->ve.p, c->stream, &c->log);
     vec_axpby(c->N, cd{1.0, 0.0}, x, cd{1.0, 0.0}, c->ve.p, c->stream, &c->log);
   }
 }
 
+// general mode (smod_arpack_general.f08:88-91): y = B^-1 A x on the device (x, y may alias)
+void dev_apply_op_general(lgpu_ctx* c, const cd* x, cd* y, int refine) {
+  block_matvec(c->G, c->A.p, c->B.p, cd{1.0, 0.0}, cd{0.0, 0.0}, x, nullptr, c->vu.p, c->stream, &c->log);
+  dev_solve(c, c->vu.p, y, refine);
+}
+
 // y = M^-1 B x on the device (x, y may alias)
 void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
+  if (c->factor_of_B) return dev_apply_op_general(c, x, y, refine);
   static const bool use_ell = [] { const char* e = std::getenv("LGPU_B_ELL"); return !(e && e[0] == '0'); }();
   if (use_ell && c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
     bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->bell_w, x, c->vu.p, c->stream,
@@ -429,9 +440,12 @@ class CudaKrylovOps final : public KrylovOps {
   int refine_;
 };
 
+// general = false: OP = (A - sigma B)^-1 B, omega = sigma + 1/nu  (smod_arpack_shift_invert.f08)
+// general = true:  OP = B^-1 A,            omega = nu              (smod_arpack_general.f08)
 int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, bool resid_on_device,
-                    double* omega_ri, double* vr_out, bool vr_on_device, lgpu_stats* stats) {
-  if (!c->assembled()) return fail(c, LGPU_ESTATE, "shift_invert: matrices not assembled");
+                    double* omega_ri, double* vr_out, bool vr_on_device, lgpu_stats* stats,
+                    bool general = false) {
+  if (!c->assembled()) return fail(c, LGPU_ESTATE, "arnoldi: matrices not assembled");
   const int n = c->N;
   if (cfg->nev <= 0 || cfg->nev >= n) return fail(c, LGPU_EINVAL, "nev out of range");
   if (cfg->ncv - cfg->nev < 1 || cfg->ncv > n || cfg->ncv > KRYLOV_MAXCOL)
@@ -442,7 +456,7 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   for (auto w : allowed) ok = ok || (w[0] == cfg->which[0] && w[1] == cfg->which[1]);
   if (!ok) return fail(c, LGPU_EINVAL, "which must be one of LM SM LR SR LI SI");
 
-  int rc = do_factorize(c, cd{cfg->sigma_re, cfg->sigma_im});
+  int rc = do_factorize(c, cd{cfg->sigma_re, cfg->sigma_im}, general);
   if (rc != LGPU_OK) return rc;
   const int ncv = cfg->ncv, nev = cfg->nev;
   c->basis = make_basis_layout(n, ncv);
@@ -470,7 +484,8 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   const double nan = std::numeric_limits<double>::quiet_NaN();
   for (int k = 0; k < nev; ++k) {
     if (k < res.nconv) {
-      const cplx om = cplx(cfg->sigma_re, cfg->sigma_im) + 1.0 / res.ritz[k];   // :157
+      const cplx om = general ? res.ritz[k]
+                              : cplx(cfg->sigma_re, cfg->sigma_im) + 1.0 / res.ritz[k];   // :157
       omega_ri[2 * k] = om.real();
       omega_ri[2 * k + 1] = om.imag();
     } else {
@@ -495,6 +510,10 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   const double t2 = now_ms();
   c->t_iter = t1 - t0;
   c->t_extract = t2 - t1;
+  if (general) {   // the factors of B are of no use to lgpu_solve / lgpu_apply_op
+    c->factorized = false;
+    c->factor_of_B = false;
+  }
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
     stats->info = res.info;
@@ -947,6 +966,14 @@ int lgpu_shift_invert(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resi
   return guarded(ctx, [&] {
     if (!cfg || !resid0_ri || !omega_ri) return fail(ctx, LGPU_EINVAL, "null argument");
     return do_shift_invert(ctx, cfg, resid0_ri, false, omega_ri, vr_ri, false, stats);
+  });
+}
+
+int lgpu_arnoldi_general(lgpu_ctx* ctx, const lgpu_arnoldi* cfg, const double* resid0_ri,
+                         double* omega_ri, double* vr_ri, lgpu_stats* stats) {
+  return guarded(ctx, [&] {
+    if (!cfg || !resid0_ri || !omega_ri) return fail(ctx, LGPU_EINVAL, "arnoldi_general: null argument");
+    return do_shift_invert(ctx, cfg, resid0_ri, false, omega_ri, vr_ri, false, stats, true);
   });
 }
 

@@ -79,6 +79,17 @@ module mod_gpu_bridge
       type(lgpu_stats), intent(out) :: stats
     end function lgpu_shift_invert
 
+    integer(c_int) function lgpu_arnoldi_general(ctx, cfg, resid0, omega, vr, stats) &
+      bind(C, name="lgpu_arnoldi_general")
+      import :: c_ptr, c_int, c_double_complex, lgpu_arnoldi, lgpu_stats
+      type(c_ptr), value :: ctx
+      type(lgpu_arnoldi), intent(in) :: cfg
+      complex(c_double_complex), intent(in) :: resid0(*)
+      complex(c_double_complex), intent(out) :: omega(*)
+      complex(c_double_complex), intent(out) :: vr(*)
+      type(lgpu_stats), intent(out) :: stats
+    end function lgpu_arnoldi_general
+
     integer(c_int) function lgpu_inverse_iteration(ctx, sigma_re, sigma_im, maxiter, tol, omega, vr, stats) &
       bind(C, name="lgpu_inverse_iteration")
       import :: c_ptr, c_int, c_double, c_double_complex, lgpu_stats
@@ -113,6 +124,7 @@ module mod_gpu_bridge
   type(c_ptr), save :: gpu_ctx = c_null_ptr
 
   public :: build_matrices_gpu, solve_arpack_shift_invert_gpu, materialise_matrix_gpu
+  public :: solve_arpack_general_gpu
   public :: inverse_iteration_gpu, residuals_gpu, base_eigenfunctions_gpu
 
 contains
@@ -274,6 +286,51 @@ contains
     call arpack_cfg%parse_zneupd_info()
     call arpack_cfg%parse_finished_stats()
   end subroutine solve_arpack_shift_invert_gpu
+
+
+  !> Drop-in for solve_arpack_general (src/solvers/arnoldi/smod_arpack_general.f08:14-131):
+  !! OP = B^-1 A, arpack_cfg built by new_arpack_config(mode=1, bmat="I") as before.
+  subroutine solve_arpack_general_gpu(arpack_cfg, omega, vr)
+    use mod_arpack_type, only: arpack_t
+    use mod_logging, only: logger, str
+    type(arpack_t), intent(inout) :: arpack_cfg
+    complex(dp), intent(out) :: omega(:)
+    complex(dp), intent(out) :: vr(:, :)
+
+    type(lgpu_arnoldi) :: ca
+    type(lgpu_stats) :: st
+    character(len=2) :: which
+    logical :: converged
+    integer :: rc
+
+    ca%nev = arpack_cfg%get_nev()
+    ca%ncv = arpack_cfg%get_ncv()
+    ca%maxiter = arpack_cfg%get_maxiter()
+    which = arpack_cfg%get_which()
+    ca%which(1) = which(1:1)
+    ca%which(2) = which(2:2)
+    ca%pad = 0
+    ca%tol = arpack_cfg%get_tolerance()
+    ca%sigma_re = 0.0d0
+    ca%sigma_im = 0.0d0
+    ca%refine_steps = 0
+    ca%reserved = 0
+
+    rc = lgpu_arnoldi_general(gpu_ctx, ca, arpack_cfg%residual, omega, vr, st)
+    if (rc /= 0) then
+      call logger%error("legolas_b200: lgpu_arnoldi_general failed with " // str(rc))
+      return
+    end if
+    arpack_cfg%info = st%info
+    arpack_cfg%iparam(5) = st%nconv
+    arpack_cfg%iparam(9) = st%n_op
+    arpack_cfg%iparam(10) = st%n_bx
+    arpack_cfg%iparam(11) = st%n_reorth
+    call arpack_cfg%parse_znaupd_info(converged)
+    arpack_cfg%info = 0
+    call arpack_cfg%parse_zneupd_info()
+    call arpack_cfg%parse_finished_stats()
+  end subroutine solve_arpack_general_gpu
 
 
   !> Drop-in for the body of inverse_iteration (src/solvers/smod_inverse_iteration.f08:16-205);

@@ -13,6 +13,7 @@ driven exactly like the reference's call sites:
   band LU / solve ............ src/solvers/mod_linear_systems.f08:67-127
   banded matvec .............. src/matrices/datastructure/mod_banded_operations.f08:18-41
   QR-invert .................. src/solvers/smod_qr_invert.f08:46-135
+  solve_arpack_general ....... src/solvers/arnoldi/smod_arpack_general.f08:14-131
 
 Parity of this file is pinned by the reference's own known answers
 (``tests/unit_tests/mod_test_solvers_arpack_shift_invert.pf:16-27``) and the
@@ -124,6 +125,36 @@ def shift_invert(A_band, B_band, kl, ku, sigma, nev, ncv=0, maxiter=0, tol=0.0, 
     stats["t_iter"] = time.perf_counter() - t0
     stats["nconv"] = nconv
     omega = sigma + 1.0 / nu                   # :157
+    if return_stats:
+        return omega, vr, stats
+    return omega, vr
+
+
+def arnoldi_general(A_band, B_band, kl, ku, nev, ncv=0, maxiter=0, tol=0.0, which="LM", v0=None,
+                    return_stats=False):
+    """Restatement of ``solve_arpack_general`` (src/solvers/arnoldi/smod_arpack_general.f08:14-131):
+    ARPACK mode 1, bmat = "I" on OP = B^-1 A; every OP*x is ``zgbmv`` with A (:88) followed by
+    ``solve_linear_system_complex_banded`` = ``zgbsv`` on a fresh copy of B (:89-91,
+    src/solvers/mod_linear_systems.f08:33-62) -- i.e. the reference factorises B again on every
+    application; the factors are the same each time, so one ``zgbtrf`` + ``zgbtrs`` per
+    application is arithmetically identical.  The Ritz values are omega themselves."""
+    n = A_band.shape[1]
+    ncv, maxiter, tol = arpack_defaults(n, nev, ncv, maxiter, tol)
+    if v0 is None:
+        v0 = zlarnv(n)
+    lu = BandedLU(B_band, kl, ku)
+    stats = {"n_op": 0, "lu_info": int(lu.info)}
+
+    def op(x):
+        stats["n_op"] += 1
+        return lu.solve(banded_matvec(A_band, kl, ku, x))
+
+    OP = LinearOperator((n, n), matvec=op, dtype=np.complex128)
+    try:
+        omega, vr = eigs(OP, k=nev, which=which, ncv=ncv, maxiter=maxiter, tol=tol, v0=v0.copy())
+    except ArpackNoConvergence as exc:
+        omega, vr = exc.eigenvalues, exc.eigenvectors
+    stats["nconv"] = len(omega)
     if return_stats:
         return omega, vr, stats
     return omega, vr

@@ -168,3 +168,56 @@ def test_eigenfunctions_need_an_assembled_grid(ctx):
     ctx.import_coo("B", 176, r, c, v)                    # imported matrices carry no grid
     with pytest.raises(lb.LgpuError):
         ctx.eigenfunctions(np.zeros((176, 1), dtype=np.complex128), np.array([1], dtype=np.int32))
+
+
+# ---- row N3: ARPACK general mode (OP = B^-1 A), tests/unit_tests/mod_test_solvers_arpack_general.pf
+@pytest.mark.parametrize("which,idxs", [("LM", [4, 7, 9, 10]), ("SM", [1, 2, 3, 5]), ("LR", [7, 8, 9, 10]),
+                                        ("SR", [1, 2, 3, 4]), ("LI", [4, 7, 9, 10]), ("SI", [1, 2, 3, 8])])
+def test_arnoldi_general_pfunit_known_answers(ctx, which, idxs):
+    from test_oracle_golden import EXPECTED_10, pencil_10
+    a, b = pencil_10()
+    # embed in N = 16: six decoupled rows whose eigenvalue is never among the four wanted ones
+    n = 16
+    pad = 1.0e-3 * (1 + 1j) if which[0] == "L" else 1.0e3 * (1 + 1j)
+    ap = np.zeros((n, n), dtype=complex)
+    bp = np.zeros((n, n), dtype=complex)
+    ap[:10, :10], bp[:10, :10] = a, b
+    for i in range(10, n):
+        ap[i, i], bp[i, i] = pad, 1.0
+    for M, label in ((ap, "A"), (bp, "B")):
+        r, c = np.nonzero(M)
+        ctx.import_coo(label, n, r + 1, c + 1, M[r, c])
+    sv = lb.SolverSettings(solver="arnoldi", arpack_mode="general", number_of_eigenvalues=4,
+                           maxiter=500, which_eigenvalues=which)
+    cfg = lb.new_arpack_config(n, 1, "I", sv)
+    omega, vr, stats = ctx.arnoldi_general(cfg)
+    assert stats["nconv"] == 4
+    order = np.argsort(omega.real)
+    omega, vr = omega[order], vr[:, order]
+    assert np.abs(omega - EXPECTED_10[np.array(idxs) - 1]).max() < 1e-12
+    # A v = omega B v on the original pencil
+    for k in range(4):
+        assert np.linalg.norm(ap @ vr[:, k] - omega[k] * (bp @ vr[:, k])) < 1e-10
+    # the factors of B are not left behind as if they were those of A - sigma B
+    with pytest.raises(lb.LegolasError):
+        ctx.solve(np.ones(n, dtype=complex))
+
+
+@pytest.mark.parametrize("name,gridpts,which,nev", [("adiabatic_homo", 31, "LM", 6),
+                                                     ("kelvin_helmholtz_cd", 51, "LM", 4)])
+def test_arnoldi_general_matches_oracle(ctx, name, gridpts, which, nev):
+    """solve_evp(arpack_mode="general") on assembled matrices against the oracle's ARPACK run."""
+    s, grid, fields = getattr(heq, name)(gridpts)
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="general", number_of_eigenvalues=nev,
+                                  which_eigenvalues=which, maxiter=2000)
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    omega, vr, cfg, stats = lb.solve_evp(mats, s)
+    so, go, xgo, fo = getattr(oeq, name + "_eq")(gridpts=gridpts)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    om_o, _, st_o = osolvers.arnoldi_general(A.to_band(), B.to_band(), 31, 31, nev, which=which,
+                                             maxiter=2000, return_stats=True)
+    assert stats["nconv"] == st_o["nconv"] == nev
+    for w in omega:
+        assert np.min(np.abs(om_o - w)) <= 1e-8 * abs(w)
+    res = ctx.residuals(omega, vr)
+    assert res.max() < 1e-9

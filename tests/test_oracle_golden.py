@@ -234,6 +234,20 @@ def test_shift_invert_pfunit_known_answers(sigma, idxs):
     assert np.abs(omega - EXPECTED_10[np.array(idxs) - 1]).max() < 1e-12
 
 
+# ---- tests/unit_tests/mod_test_solvers_arpack_general.pf:15-26,93-178 (same pencil, mode "general")
+GENERAL_CASES = [("LM", [4, 7, 9, 10]), ("SM", [1, 2, 3, 5]), ("LR", [7, 8, 9, 10]),
+                 ("SR", [1, 2, 3, 4]), ("LI", [4, 7, 9, 10]), ("SI", [1, 2, 3, 8])]
+
+
+@pytest.mark.parametrize("which,idxs", GENERAL_CASES)
+def test_arnoldi_general_pfunit_known_answers(which, idxs):
+    a, b = pencil_10()
+    omega, _ = solvers.arnoldi_general(dense_to_band(a, 3, 3), dense_to_band(b, 3, 3), 3, 3, 4,
+                                       maxiter=500, which=which)
+    omega = omega[np.argsort(omega.real)]
+    assert np.abs(omega - EXPECTED_10[np.array(idxs) - 1]).max() < 1e-12
+
+
 def test_zlarnv_is_deterministic_and_uniform():
     v = solvers.zlarnv(1000)
     assert np.array_equal(v, solvers.zlarnv(1000))
