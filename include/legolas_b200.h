@@ -56,7 +56,9 @@ enum lgpu_field {
  * boundary manager (src/boundaries/mod_boundary_manager.f08:87-107). */
 typedef struct {
   int32_t gridpts;            /* settings%grid%get_gridpts()                              */
-  int32_t physics_type;       /* 0 "mhd" (8 eqs), 1 "hd" (5), 2 "hd-1d" (3)               */
+  int32_t physics_type;       /* 0 "mhd" (8 eqs), 1 "hd" (5: rho,v1,v2,v3,T), 2 "hd-1d" (3: rho,v1,T);
+                                 N = gridpts * 2 * nb_eqs and every vector / index crossing this ABI
+                                 uses that numbering (src/settings/mod_settings.f08:69-86)        */
   int32_t geometry;           /* 0 Cartesian (eps=1, deps=0), 1 cylindrical (eps=x, deps=1)*/
   int32_t incompressible;     /* gamma := 1e12, src/settings/mod_physics_settings.f08:90  */
   int32_t flow, resistivity, cooling, heating, conduction, perpendicular_conduction;
@@ -188,7 +190,8 @@ int lgpu_residuals(lgpu_ctx* ctx, int32_t nev, const double* omega_ri, const dou
  *            assemble_eigenfunction + retransform_eigenfunction (mod_ef_assembly.f08:16-106) for all 8
  *            variables and the selected eigenvectors.  vr_ri: N x (max idx) complex host, ld = N;
  *            idxs: nsel 1-based column indices (idxs_to_assemble); out_ri: complex
- *            [8][nsel][2*gridpts-1], i.e. quantities(:, i) of variable p at ((p*nsel + i)*npts). */
+ *            [nb_eqs][nsel][2*gridpts-1], i.e. quantities(:, i) of variable p (state-vector order) at
+ *            ((p*nsel + i)*npts). */
 int lgpu_eigenfunctions(lgpu_ctx* ctx, const double* vr_ri, int32_t nsel, const int32_t* idxs, double* out_ri);
 int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t maxiter, double tol,
                            double* omega_ri, double* vr_ri, lgpu_stats* stats);

@@ -34,6 +34,9 @@ assert len(FIELD_NAMES) == N_FIELDS
 
 ZLARNV_SEED = (2022, 9, 30, 179)   # mod_arpack_type.f08:206
 PHYSICS_TYPES = {"mhd": 0, "hd": 1, "hd-1d": 2}
+# src/settings/mod_settings.f08:69-86
+STATE_VECTORS = {"mhd": ("rho", "v1", "v2", "v3", "T", "a1", "a2", "a3"),
+                 "hd": ("rho", "v1", "v2", "v3", "T"), "hd-1d": ("rho", "v1", "T")}
 GEOMETRIES = {"Cartesian": 0, "cylindrical": 1}
 BOUNDARY_TYPES = {"wall": 0, "wall_weak": 1}
 ALLOWED_WHICH = ("LM", "SM", "LR", "SR", "LI", "SI")
@@ -198,6 +201,9 @@ class Context:
         self._h = handle
         self.device = device
         self._keepalive = None
+        # 2 * nb_eqs and the state vector of the resident matrices (mod_settings.f08:69-86)
+        self.dim_subblock = 16
+        self.state_vector = STATE_VECTORS["mhd"]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -278,6 +284,12 @@ class Context:
         cs = settings.to_c()
         self._check(self._lib.lgpu_assemble(self._h, C.byref(cs), grid.ctypes.data,
                                             gauss_grid.ctypes.data, ptrs), "assemble")
+        self._resident(settings)
+
+    def _resident(self, settings: Optional[Settings]):
+        ptype = settings.physics_type if settings is not None else "mhd"
+        self.state_vector = STATE_VECTORS[ptype]
+        self.dim_subblock = 2 * len(self.state_vector)
 
     def assemble_device(self, settings: Settings, grid_ptr: int, gauss_ptr: int, field_ptrs):
         """Same with device pointers (inputs already resident in HBM)."""
@@ -287,12 +299,15 @@ class Context:
         cs = settings.to_c()
         self._check(self._lib.lgpu_assemble_device(self._h, C.byref(cs), C.c_void_p(grid_ptr),
                                                    C.c_void_p(gauss_ptr), ptrs), "assemble_device")
+        self._resident(settings)
 
     def export_blocks(self, which: str) -> np.ndarray:
-        """(gridpts, 3, 16, 16) complex: [sub, diag, super] blocks; [b, t, i, j] = row i, col j."""
+        """(gridpts, 3, d, d) complex, d = dim_subblock (16 mhd / 10 hd / 6 hd-1d): [sub, diag, super]
+        blocks in the reference's numbering; [b, t, i, j] = row i, col j."""
         n = self.dim
-        g = n // 16
-        raw = np.empty((g, 3, 16, 16), dtype=np.complex128)   # device blocks are column-major
+        d = self.dim_subblock
+        g = n // d
+        raw = np.empty((g, 3, d, d), dtype=np.complex128)   # device blocks are column-major
         self._check(self._lib.lgpu_export_blocks(self._h, _which(which), raw.ctypes.data),
                     "export_blocks")
         return np.ascontiguousarray(raw.transpose(0, 1, 3, 2))
@@ -315,6 +330,7 @@ class Context:
         vals = np.ascontiguousarray(vals, dtype=np.complex128)
         self._check(self._lib.lgpu_import_coo(self._h, _which(which), n, len(rows), rows.ctypes.data,
                                               cols.ctypes.data, vals.ctypes.data), "import_coo")
+        self._resident(None)
 
     # ---- linear algebra pieces
     def factorize(self, sigma: complex) -> int:
@@ -391,15 +407,16 @@ class Context:
                                              res.ctypes.data_as(C.POINTER(C.c_double))), "residuals")
         return res
 
-    def eigenfunctions(self, vr, idxs, state_vector=("rho", "v1", "v2", "v3", "T", "a1", "a2", "a3")) -> dict:
-        """base_ef_t%assemble for every variable (src/eigenfunctions/mod_base_efs.f08:35-61):
+    def eigenfunctions(self, vr, idxs, state_vector=None) -> dict:
+        """base_ef_t%assemble for every variable of the state vector (src/eigenfunctions/mod_base_efs.f08:35-61):
         {name: (2 G - 1, len(idxs)) complex}; ``idxs`` are 1-based columns of ``vr`` (idxs_to_assemble)."""
         vr = np.asfortranarray(vr, dtype=np.complex128)
         idxs = np.ascontiguousarray(idxs, dtype=np.int32)
         if vr.shape[0] != self.dim or (len(idxs) and (idxs.min() < 1 or idxs.max() > vr.shape[1])):
             raise LegolasError("eigenfunctions: eigenvector array / indices do not match the matrices")
-        npts = 2 * (self.dim // 16) - 1
-        out = np.zeros((8, len(idxs), npts), dtype=np.complex128)
+        state_vector = state_vector or self.state_vector
+        npts = 2 * (self.dim // self.dim_subblock) - 1
+        out = np.zeros((self.dim_subblock // 2, len(idxs), npts), dtype=np.complex128)
         self._check(self._lib.lgpu_eigenfunctions(self._h, vr.ctypes.data, len(idxs),
                                                   idxs.ctypes.data_as(C.POINTER(C.c_int32)), out.ctypes.data),
                     "eigenfunctions")

@@ -77,7 +77,16 @@ struct lgpu_ctx {
   // matrices
   lgpu_settings settings{};
   int G = 0;            // block rows (gridpts)
-  int N = 0;            // matrix dimension
+  int N = 0;            // device dimension: 16 rows per grid point for every physics type
+  // hd / hd-1d (src/settings/mod_settings.f08:69-86): the reference numbers 2 nb_eqs rows per grid
+  // point; on the device an absent variable leaves an empty slot.  cmap[r] = device row (within a
+  // block) of compact row r; all vectors and indices crossing the C ABI use the compact numbering.
+  int dsub = BLK;
+  int cmap[BLK] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+  uint32_t padmask = 0; // device rows of a block that belong to no variable
+  int Nc() const { return G * dsub; }
+  bool compact() const { return dsub != BLK; }
+  DevBuf<cd> cbuf;      // staging for compact <-> device layout translation
   bool have[2] = {false, false};
   DevBuf<cd> A, B;
   DevBuf<uint32_t> masks, natmasks;
@@ -123,7 +132,7 @@ struct lgpu_ctx {
     SluDevice d{};
     d.A = factor_of_B ? B.p : A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
     d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
-    d.sync = d_sync.p; d.epoch = &solve_epoch;
+    d.sync = d_sync.p; d.epoch = &solve_epoch; d.padmask = padmask;
     return d;
   }
 };
@@ -151,6 +160,78 @@ int guarded(lgpu_ctx* ctx, F&& body) {
 int fail(lgpu_ctx* ctx, int code, const std::string& msg) {
   ctx->err = msg;
   return code;
+}
+
+struct RowMap { int r[BLK]; };
+
+// dst (device layout, ld = 16 G) <- src (compact, ld = dsub G); empty slots are zeroed
+__global__ void expand_rows_kernel(const cd* __restrict__ src, cd* __restrict__ dst, int G, int dsub, RowMap inv,
+                                   int ncols) {
+  const size_t n = static_cast<size_t>(G) * BLK, total = n * ncols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t col = i / n, row = i % n;
+    const int q = inv.r[row % BLK];
+    dst[i] = q >= 0 ? src[col * (static_cast<size_t>(G) * dsub) + (row / BLK) * dsub + q] : cd{0.0, 0.0};
+  }
+}
+
+// dst (compact) <- src (device layout)
+__global__ void compact_rows_kernel(const cd* __restrict__ src, cd* __restrict__ dst, int G, int dsub, RowMap fwd,
+                                    int ncols) {
+  const size_t nc = static_cast<size_t>(G) * dsub, total = nc * ncols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t col = i / nc, row = i % nc;
+    dst[i] = src[col * (static_cast<size_t>(G) * BLK) + (row / dsub) * BLK + fwd.r[row % dsub]];
+  }
+}
+
+int map_grid(size_t total) { return static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 8)); }
+
+// ncols vectors in the reference's numbering (host or device memory) -> device layout
+void vec_in(lgpu_ctx* c, const void* src, bool src_on_device, cd* dst, int ncols = 1) {
+  const cudaMemcpyKind kind = src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (!c->compact()) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(cd) * c->N * ncols, kind, c->stream));
+    return;
+  }
+  const size_t cnt = static_cast<size_t>(c->Nc()) * ncols;
+  const cd* from = static_cast<const cd*>(src);
+  if (!src_on_device) {
+    c->cbuf.ensure(cnt);
+    CUDA_CHECK(cudaMemcpyAsync(c->cbuf.p, src, sizeof(cd) * cnt, kind, c->stream));
+    from = c->cbuf.p;
+  }
+  RowMap inv;
+  for (int i = 0; i < BLK; ++i) inv.r[i] = -1;
+  for (int q = 0; q < c->dsub; ++q) inv.r[c->cmap[q]] = q;
+  const size_t total = static_cast<size_t>(c->N) * ncols;
+  expand_rows_kernel<<<map_grid(total), 256, 0, c->stream>>>(from, dst, c->G, c->dsub, inv, ncols);
+  CUDA_CHECK(cudaGetLastError());
+  c->log.launches += 1;
+}
+
+// device layout -> ncols vectors in the reference's numbering (host or device memory); the copy to
+// the host is asynchronous on the context's stream like the plain one
+void vec_out(lgpu_ctx* c, const cd* src, void* dst, bool dst_on_device, int ncols = 1) {
+  const cudaMemcpyKind kind = dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (!c->compact()) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(cd) * c->N * ncols, kind, c->stream));
+    return;
+  }
+  const size_t cnt = static_cast<size_t>(c->Nc()) * ncols;
+  cd* to = static_cast<cd*>(dst);
+  if (!dst_on_device) {
+    c->cbuf.ensure(cnt);
+    to = c->cbuf.p;
+  }
+  RowMap fwd;
+  for (int i = 0; i < BLK; ++i) fwd.r[i] = i < c->dsub ? c->cmap[i] : 0;
+  compact_rows_kernel<<<map_grid(cnt), 256, 0, c->stream>>>(src, to, c->G, c->dsub, fwd, ncols);
+  CUDA_CHECK(cudaGetLastError());
+  c->log.launches += 1;
+  if (!dst_on_device) CUDA_CHECK(cudaMemcpyAsync(dst, to, sizeof(cd) * cnt, kind, c->stream));
 }
 
 void ensure_vectors(lgpu_ctx* c) {
@@ -183,12 +264,23 @@ KrylovWork kwork(lgpu_ctx* c) {
 
 int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const double* d_gauss,
                 const FieldPtrs& fields) {
-  if (s->physics_type != 0)
-    return fail(c, LGPU_EINVAL, "only physics_type 0 (mhd, 8 equations) is built so far");
+  if (s->physics_type < 0 || s->physics_type > 2)
+    return fail(c, LGPU_EINVAL, "physics_type must be 0 (mhd), 1 (hd) or 2 (hd-1d)");
   const int G = s->gridpts;
   c->settings = *s;
   c->G = G;
   c->N = G * BLK;
+  {
+    int slots[8];
+    const int nb_eqs = state_positions(s->physics_type, slots);
+    c->dsub = 2 * nb_eqs;
+    c->padmask = 0xffffu;
+    for (int q = 0; q < nb_eqs; ++q) {
+      c->cmap[2 * q] = 2 * slots[q];
+      c->cmap[2 * q + 1] = 2 * slots[q] + 1;
+      c->padmask &= ~(3u << (2 * slots[q]));
+    }
+  }
   c->factorized = false;
   const size_t nblk = static_cast<size_t>(G) * 3 * BLK2;
   c->A.ensure(nblk);
@@ -447,8 +539,8 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
                     bool general = false) {
   if (!c->assembled()) return fail(c, LGPU_ESTATE, "arnoldi: matrices not assembled");
   const int n = c->N;
-  if (cfg->nev <= 0 || cfg->nev >= n) return fail(c, LGPU_EINVAL, "nev out of range");
-  if (cfg->ncv - cfg->nev < 1 || cfg->ncv > n || cfg->ncv > KRYLOV_MAXCOL)
+  if (cfg->nev <= 0 || cfg->nev >= c->Nc()) return fail(c, LGPU_EINVAL, "nev out of range");
+  if (cfg->ncv - cfg->nev < 1 || cfg->ncv > c->Nc() || cfg->ncv > KRYLOV_MAXCOL)
     return fail(c, LGPU_EINVAL, "ncv out of range (nev + 1 <= ncv <= min(N, 128))");
   if (cfg->maxiter <= 0) return fail(c, LGPU_EINVAL, "maxiter must be positive");
   static const char* allowed[6] = {"LM", "SM", "LR", "SR", "LI", "SI"};
@@ -468,9 +560,7 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   c->Z.ensure(static_cast<size_t>(n) * nev);
   ensure_krylov_work(c);
   CUDA_CHECK(cudaMemsetAsync(c->Hdev.p, 0, sizeof(cd) * ncv * ncv, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(c->resid.p, resid0, sizeof(cd) * n,
-                             resid_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                             c->stream));
+  vec_in(c, resid0, resid_on_device, c->resid.p);
 
   IramConfig ic;
   ic.nev = nev; ic.ncv = ncv; ic.maxiter = cfg->maxiter; ic.tol = cfg->tol;
@@ -494,15 +584,15 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
     }
   }
   if (vr_out) {
-    const size_t got = static_cast<size_t>(n) * res.nconv, all = static_cast<size_t>(n) * nev;
+    const size_t got = static_cast<size_t>(c->Nc()) * res.nconv, all = static_cast<size_t>(c->Nc()) * nev;
     if (vr_on_device) {
-      CUDA_CHECK(cudaMemcpyAsync(vr_out, c->Z.p, got * sizeof(cd), cudaMemcpyDeviceToDevice, c->stream));
+      if (res.nconv > 0) vec_out(c, c->Z.p, vr_out, true, res.nconv);
       if (all > got)
         CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<cd*>(vr_out) + got, 0, (all - got) * sizeof(cd),
                                    c->stream));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
     } else {
-      CUDA_CHECK(cudaMemcpyAsync(vr_out, c->Z.p, got * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
+      if (res.nconv > 0) vec_out(c, c->Z.p, vr_out, false, res.nconv);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       if (all > got) std::memset(vr_out + 2 * got, 0, (all - got) * sizeof(cd));
     }
@@ -631,7 +721,7 @@ int lgpu_assemble_device(lgpu_ctx* ctx, const lgpu_settings* s, const double* ba
 
 int lgpu_matrix_dim(lgpu_ctx* ctx, int32_t* n) {
   if (!ctx || !n) return LGPU_EINVAL;
-  *n = ctx->N;
+  *n = ctx->Nc();   // the reference's dim_matrix = gridpts * 2 * nb_eqs
   return LGPU_OK;
 }
 
@@ -640,6 +730,22 @@ int lgpu_export_blocks(lgpu_ctx* ctx, int32_t which, double* blocks_ri) {
     if (which < 0 || which > 1 || !blocks_ri) return fail(ctx, LGPU_EINVAL, "bad argument");
     if (!ctx->have[which]) return fail(ctx, LGPU_ESTATE, "matrix not available");
     const size_t cnt = static_cast<size_t>(ctx->G) * 3 * BLK2;
+    if (ctx->compact()) {   // (G, 3, dsub, dsub) tiles in the reference's numbering
+      std::vector<cd> blocks(cnt);
+      CUDA_CHECK(cudaMemcpyAsync(blocks.data(), which ? ctx->B.p : ctx->A.p, cnt * sizeof(cd),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      const int d = ctx->dsub;
+      for (size_t t = 0; t < static_cast<size_t>(ctx->G) * 3; ++t)
+        for (int j = 0; j < d; ++j)
+          for (int i = 0; i < d; ++i) {
+            const cd v = blocks[t * BLK2 + ctx->cmap[j] * BLK + ctx->cmap[i]];
+            double* dst = blocks_ri + 2 * (t * d * d + static_cast<size_t>(j) * d + i);
+            dst[0] = v.x;
+            dst[1] = v.y;
+          }
+      return LGPU_OK;
+    }
     CUDA_CHECK(cudaMemcpyAsync(blocks_ri, which ? ctx->B.p : ctx->A.p, cnt * sizeof(cd),
                                cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -664,6 +770,9 @@ int lgpu_export_coo(lgpu_ctx* ctx, int32_t which, int64_t* nnz, int32_t* rows, i
                                cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     auto bit = [](const uint32_t* w, int idx) { return (w[idx >> 5] >> (idx & 31)) & 1u; };
+    int inv[BLK];   // device row within a block -> row in the reference's numbering
+    for (int i = 0; i < BLK; ++i) inv[i] = 0;
+    for (int q = 0; q < ctx->dsub; ++q) inv[ctx->cmap[q]] = q;
     int64_t count = 0;
     const bool fill = rows && cols && vals_ri;
     for (int b = 0; b < G; ++b) {
@@ -695,8 +804,8 @@ int lgpu_export_coo(lgpu_ctx* ctx, int32_t which, int64_t* nnz, int32_t* rows, i
         for (int e = 0; e < ne; ++e) {
           if (fill) {
             const cd v = blocks[(static_cast<size_t>(b) * 3 + ent_tile[e]) * BLK2 + ent_col[e] * BLK + i];
-            rows[count] = b * BLK + i + 1;
-            cols[count] = (b + ent_tile[e] - 1) * BLK + ent_col[e] + 1;
+            rows[count] = b * ctx->dsub + inv[i] + 1;
+            cols[count] = (b + ent_tile[e] - 1) * ctx->dsub + inv[ent_col[e]] + 1;
             vals_ri[2 * count] = v.x;
             vals_ri[2 * count + 1] = v.y;
           }
@@ -739,6 +848,9 @@ int lgpu_import_coo(lgpu_ctx* ctx, int32_t which, int32_t n, int64_t nnz, const 
     }
     ctx->G = G;
     ctx->N = n;
+    ctx->dsub = BLK;   // imported matrices are in the full 16-wide numbering
+    for (int i = 0; i < BLK; ++i) ctx->cmap[i] = i;
+    ctx->padmask = 0;
     ctx->factorized = false;
     if (ctx->splan.n != G) ctx->splan.n = 0;
     (which ? ctx->B : ctx->A).ensure(cnt);
@@ -766,10 +878,9 @@ int lgpu_solve(lgpu_ctx* ctx, const double* rhs_ri, double* x_ri, int32_t refine
   return guarded(ctx, [&] {
     if (!ctx->factorized) return fail(ctx, LGPU_ESTATE, "solve: call lgpu_factorize first");
     if (!rhs_ri || !x_ri) return fail(ctx, LGPU_EINVAL, "null argument");
-    const size_t bytes = sizeof(cd) * ctx->N;
-    CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, rhs_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    vec_in(ctx, rhs_ri, false, ctx->vx.p);
     dev_solve(ctx, ctx->vx.p, ctx->vy.p, refine_steps);
-    CUDA_CHECK(cudaMemcpyAsync(x_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    vec_out(ctx, ctx->vy.p, x_ri, false);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LGPU_OK;
   });
@@ -780,12 +891,11 @@ int lgpu_matvec(lgpu_ctx* ctx, int32_t which, const double* x_ri, double* y_ri) 
     if (which < 0 || which > 1 || !x_ri || !y_ri) return fail(ctx, LGPU_EINVAL, "bad argument");
     if (!ctx->assembled()) return fail(ctx, LGPU_ESTATE, "matvec: matrices not assembled");
     ensure_vectors(ctx);
-    const size_t bytes = sizeof(cd) * ctx->N;
-    CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, x_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    vec_in(ctx, x_ri, false, ctx->vx.p);
     block_matvec(ctx->G, ctx->A.p, ctx->B.p, cd{which == 0 ? 1.0 : 0.0, 0.0},
                  cd{which == 1 ? 1.0 : 0.0, 0.0}, ctx->vx.p, nullptr, ctx->vy.p, ctx->stream,
                  &ctx->log);
-    CUDA_CHECK(cudaMemcpyAsync(y_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    vec_out(ctx, ctx->vy.p, y_ri, false);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LGPU_OK;
   });
@@ -795,10 +905,9 @@ int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refin
   return guarded(ctx, [&] {
     if (!ctx->factorized) return fail(ctx, LGPU_ESTATE, "apply_op: call lgpu_factorize first");
     if (!x_ri || !y_ri) return fail(ctx, LGPU_EINVAL, "null argument");
-    const size_t bytes = sizeof(cd) * ctx->N;
-    CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, x_ri, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    vec_in(ctx, x_ri, false, ctx->vx.p);
     dev_apply_op(ctx, ctx->vx.p, ctx->vy.p, refine_steps);
-    CUDA_CHECK(cudaMemcpyAsync(y_ri, ctx->vy.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    vec_out(ctx, ctx->vy.p, y_ri, false);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LGPU_OK;
   });
@@ -831,12 +940,10 @@ int lgpu_residuals(lgpu_ctx* ctx, int32_t nev, const double* omega_ri, const dou
     ensure_krylov_work(ctx);
     ctx->log.stream = ctx->stream;
     const KrylovWork kw = kwork(ctx);
-    const size_t bytes = sizeof(cd) * ctx->N;
     for (int k = 0; k < nev; ++k) {
       const cd om{omega_ri[2 * k], omega_ri[2 * k + 1]};
       if (std::fabs(om.x) <= DP_LIMIT && std::fabs(om.y) <= DP_LIMIT) { res[k] = 0.0; continue; }   // is_zero
-      CUDA_CHECK(cudaMemcpyAsync(ctx->vx.p, vr_ri + 2 * static_cast<size_t>(k) * ctx->N, bytes,
-                                 cudaMemcpyHostToDevice, ctx->stream));
+      vec_in(ctx, vr_ri + 2 * static_cast<size_t>(k) * ctx->Nc(), false, ctx->vx.p);
       // y = A v - omega B v
       block_matvec(ctx->G, ctx->A.p, ctx->B.p, cd{1.0, 0.0}, cd{-om.x, -om.y}, ctx->vx.p, nullptr, ctx->vy.p,
                    ctx->stream, &ctx->log);
@@ -863,17 +970,21 @@ int lgpu_eigenfunctions(lgpu_ctx* ctx, const double* vr_ri, int32_t nsel, const 
     ctx->ef_out.ensure(static_cast<size_t>(8) * npts * nsel);
     ctx->ef_idx.ensure(nsel);
     std::vector<int32_t> local(nsel);
+    const size_t nc = static_cast<size_t>(ctx->Nc());
     for (int s = 0; s < nsel; ++s) {
       if (idxs[s] < 1) return fail(ctx, LGPU_EINVAL, "eigenfunctions: indices are 1-based");
       local[s] = s;   // the selected columns are packed on the way to the device
-      CUDA_CHECK(cudaMemcpyAsync(ctx->ef_in.p + n * s, vr_ri + 2 * n * static_cast<size_t>(idxs[s] - 1), sizeof(cd) * n,
-                                 cudaMemcpyHostToDevice, ctx->stream));
+      vec_in(ctx, vr_ri + 2 * nc * static_cast<size_t>(idxs[s] - 1), false, ctx->ef_in.p + n * s);
     }
     CUDA_CHECK(cudaMemcpyAsync(ctx->ef_idx.p, local.data(), sizeof(int32_t) * nsel, cudaMemcpyHostToDevice, ctx->stream));
     ctx->log.stream = ctx->stream;
     assemble_eigenfunctions(ctx->G, ctx->settings.geometry, ctx->grid_copy.p, ctx->ef_in.p, n, nsel, ctx->ef_idx.p,
                             ctx->ef_out.p, ctx->stream, &ctx->log);
-    CUDA_CHECK(cudaMemcpyAsync(out_ri, ctx->ef_out.p, sizeof(cd) * 8 * npts * nsel, cudaMemcpyDeviceToHost, ctx->stream));
+    // one slab per variable of the active state vector, in state-vector order
+    const size_t slab = static_cast<size_t>(npts) * nsel;
+    for (int q = 0; q < ctx->dsub / 2; ++q)
+      CUDA_CHECK(cudaMemcpyAsync(out_ri + 2 * slab * q, ctx->ef_out.p + slab * (ctx->cmap[2 * q] / 2), sizeof(cd) * slab,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return LGPU_OK;
   });
@@ -905,8 +1016,8 @@ int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int3
     };
     // start vector: (A - sigma B)^-1 1
     {
-      std::vector<cd> ones(static_cast<size_t>(n), cd{1.0, 0.0});
-      CUDA_CHECK(cudaMemcpyAsync(x, ones.data(), sizeof(cd) * n, cudaMemcpyHostToDevice, c->stream));
+      std::vector<cd> ones(static_cast<size_t>(c->Nc()), cd{1.0, 0.0});
+      vec_in(c, ones.data(), false, x);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
     slu_solve(c->splan, c->sdev(), x, x, c->stream, &c->log);
@@ -932,8 +1043,8 @@ int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int3
     omega_ri[0] = ev.x;
     omega_ri[1] = ev.y;
     if (vr_ri) {
-      std::vector<cd> h(static_cast<size_t>(n));
-      CUDA_CHECK(cudaMemcpyAsync(h.data(), x, sizeof(cd) * n, cudaMemcpyDeviceToHost, c->stream));
+      std::vector<cd> h(static_cast<size_t>(c->Nc()));
+      vec_out(c, x, h.data(), false);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       // make the largest coefficient real (first maximum, as idamax)
       size_t im = 0;

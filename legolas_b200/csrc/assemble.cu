@@ -71,7 +71,12 @@ bool cond_ok(const lgpu_settings& s, int c) {
   return true;
 }
 
-// position of a variable inside the active state vector (src/settings/mod_settings.f08:69-86)
+// position of a variable inside the active state vector (src/settings/mod_settings.f08:69-86);
+// -1: not in the state vector, every term naming it is skipped (mod_matrix_elements.f08:57-59).
+// On the device every physics type is laid out in the 8-variable (16-wide) block structure: a
+// present variable keeps its mhd slot, the slots of absent variables stay empty in A and B
+// (the factorisation treats them as identity rows) and the C ABI translates indices and vectors
+// to the reference's compact numbering (state_positions).
 int var_position(int physics_type, int var) {
   static const int mhd[8] = {0, 1, 2, 3, 4, 5, 6, 7};
   static const int hd[8] = {0, 1, 2, 3, 4, -1, -1, -1};
@@ -82,6 +87,13 @@ int var_position(int physics_type, int var) {
 
 }  // namespace
 
+int state_positions(int physics_type, int slots[8]) {
+  int n = 0;
+  for (int v = 0; v < 8; ++v)
+    if (var_position(physics_type, v) >= 0) slots[n++] = v;
+  return n;
+}
+
 TermPlan build_term_plan(const lgpu_settings& s, bool natural) {
   TermPlan plan;
   std::map<std::tuple<int, int, int, int>, int> slot_of;   // (mat, p1, p2, dd) -> slot
@@ -91,8 +103,9 @@ TermPlan build_term_plan(const lgpu_settings& s, bool natural) {
     const TermDesc& t = kTerms[id];
     if (is_natural(t.module) != natural) continue;
     if (!module_active(s, t.module) || !cond_ok(s, t.cond)) continue;
-    const int p1 = var_position(s.physics_type, t.v1), p2 = var_position(s.physics_type, t.v2);
-    if (p1 < 0 || p2 < 0) continue;   // mod_matrix_elements.f08:57-59
+    if (var_position(s.physics_type, t.v1) < 0 || var_position(s.physics_type, t.v2) < 0)
+      continue;   // mod_matrix_elements.f08:57-59
+    const int p1 = t.v1, p2 = t.v2;   // device slot = mhd position
     const int mat = matrix_of(t.module), dd = t.d1 * 2 + t.d2;
     auto skey = std::make_tuple(mat, p1, p2, dd);
     auto it = slot_of.find(skey);
@@ -132,13 +145,12 @@ TermPlan build_term_plan(const lgpu_settings& s, bool natural) {
 
 std::vector<int32_t> essential_indices(const lgpu_settings& s, bool right_edge) {
   const int pt = s.physics_type;
-  const int dsub = 2 * (pt == 0 ? 8 : (pt == 1 ? 5 : 3));
+  const int dsub = BLK;   // device layout: 16-wide blocks for every physics type
   auto idx = [&](std::initializer_list<int> vars, bool odd) {
     std::vector<int32_t> out;
     for (int v : vars) {
-      int p = var_position(pt, v);
-      if (p < 0) continue;
-      int i = 2 * (p + 1);
+      if (var_position(pt, v) < 0) continue;
+      int i = 2 * (v + 1);
       if (odd) --i;
       if (right_edge) i += dsub;
       out.push_back(i);

@@ -55,6 +55,10 @@ struct FieldPtrs {
   const double* f[NFIELD];
 };
 
+// Device slots (mhd positions 0..7) of the variables in the active state vector, in state-vector
+// order (src/settings/mod_settings.f08:69-86); returns nb_eqs.
+int state_positions(int physics_type, int slots[8]);
+
 // Builds the element-integral plan (natural == false) or the natural-boundary plan.
 TermPlan build_term_plan(const lgpu_settings& s, bool natural);
 // 1-based quadblock-local indices zeroed by the essential boundary conditions

@@ -670,6 +670,7 @@ struct FactorArgs {
   int level;
   int top_size;
   int32_t* info;
+  uint32_t padmask;
 };
 
 // entry (i, j) of tile t (0 sub, 1 diag, 2 super) of block row r of A - sigma*B; the padding
@@ -677,6 +678,7 @@ struct FactorArgs {
 __device__ __forceinline__ cd m_entry(const FactorArgs& a, int r, int t, int i, int j) {
   if (r >= a.n) return cd{(t == 1 && i == j) ? 1.0 : 0.0, 0.0};
   const size_t off = (static_cast<size_t>(r) * 3 + t) * BLK2 + j * BLK + i;
+  if (t == 1 && i == j && ((a.padmask >> i) & 1u)) return cd{1.0, 0.0};   // absent variable (hd / hd-1d)
   return a.A[off] - a.sigma * a.B[off];
 }
 
@@ -1119,7 +1121,7 @@ void slu_factorize(const SluPlan& plan, const SluDevice& d, cd sigma, cudaStream
   log->begin(LK_FACTOR);
   FactorArgs a{};
   a.A = d.A; a.B = d.B; a.sigma = sigma; a.n = plan.n; a.n_pad = plan.n_pad; a.K = plan.K;
-  a.top = d.top; a.top_size = plan.top_size; a.info = d.info;
+  a.top = d.top; a.top_size = plan.top_size; a.info = d.info; a.padmask = d.padmask;
   auto rows_of = [&](int l) {
     return d.work + (l < nl ? plan.levels[l].off_rows : plan.off_rows_final) * ROW_STRIDE;
   };

@@ -101,6 +101,8 @@ struct SluDevice {
   int32_t* info;        // singular-pivot report (1-based block row, 0 = none)
   unsigned long long* sync;    // SLU_SYNC_COUNTERS device counters of the fused upper stages
   unsigned long long* epoch;   // host: solves since the counters were last cleared
+  uint32_t padmask;     // bit i: row/column i of every 16-wide block belongs to a variable that is not
+                        // in the state vector (hd / hd-1d): treated as a decoupled identity row
 };
 constexpr int SLU_SYNC_COUNTERS = 16;
 

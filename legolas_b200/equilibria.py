@@ -14,6 +14,7 @@ a ``Background`` holds callables, ``sample`` evaluates them on the Gaussian grid
   magnetothermal ......... src/equilibria/smod_equil_magnetothermal_instabilities.f08:34-86
   kelvin_helmholtz_cd .... src/equilibria/smod_equil_kelvin_helmholtz_cd.f08:32-98
   MRI_accretion .......... src/equilibria/smod_equil_MRI_accretion.f08:36-133
+  couette_flow ........... src/equilibria/smod_equil_couette_flow.f08:25-82
   units / physics ........ src/settings/mod_units.f08:161-211, src/physics/mod_thermal_conduction.f08:56-247,
                            src/physics/mod_heatloss.f08:54-139, src/physics/cooling_curves/*
 """
@@ -131,6 +132,20 @@ def adiabatic_homo(gridpts: int, k2=0.0, k3=math.pi, rho0=1.0, T0=1.0, B02=0.0, 
     s = Settings(gridpts=gridpts, geometry="Cartesian", k2=k2, k3=k3)
     grid = Grid(s, 0.0, 1.0)
     bg = Background().set(rho0=_const(rho0), T0=_const(T0), B02=_const(B02), B03=_const(B03))
+    return s, grid, bg.sample(grid.gaussian_grid)
+
+
+def couette_flow(gridpts: int, k2=0.0, k3=1.0, rho0=1.0, T0=1.0, v02=0.0, v03=1.0, viscosity_value=1.0e-3,
+                 physics_type="hd"):
+    """Plane Couette flow between two walls, flow + viscosity; runs as "hd" in the reference's
+    regression suite (tests/regression_tests/test_couette_flow_HD.py:24-50)."""
+    s = Settings(gridpts=gridpts, geometry="Cartesian", k2=k2, k3=k3, physics_type=physics_type, flow=True,
+                 viscosity=True, viscosity_value=viscosity_value)
+    grid = Grid(s, 0.0, 1.0)
+    width = 1.0
+    bg = Background().set(rho0=_const(rho0), T0=_const(T0),
+                          v02=lambda x: v02 * x / width, dv02=_const(v02 / width),
+                          v03=lambda x: v03 * x / width, dv03=_const(v03 / width))
     return s, grid, bg.sample(grid.gaussian_grid)
 
 
@@ -257,4 +272,5 @@ EQUILIBRIA = {
     "magnetothermal_instabilities": magnetothermal_instabilities,
     "kelvin_helmholtz_cd": kelvin_helmholtz_cd,
     "MRI_accretion": mri_accretion,
+    "couette_flow": couette_flow,
 }

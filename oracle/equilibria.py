@@ -12,6 +12,7 @@ Follows (reference file:line):
   magnetothermal ............ src/equilibria/smod_equil_magnetothermal_instabilities.f08:34-86
   kelvin_helmholtz_cd ....... src/equilibria/smod_equil_kelvin_helmholtz_cd.f08:32-98
   MRI_accretion ............. src/equilibria/smod_equil_MRI_accretion.f08:36-133
+  couette_flow .............. src/equilibria/smod_equil_couette_flow.f08:25-82
   on-axis grid shift ........ src/settings/mod_grid_settings.f08:112-138
   units ..................... src/settings/mod_units.f08:161-211, src/mod_physical_constants.f08
   resistivity ............... src/physics/mod_resistivity.f08:49-120
@@ -123,6 +124,21 @@ def adiabatic_homo_eq(gridpts=51, k2=0.0, k3=DPI, cte_rho0=1.0, cte_T0=1.0, cte_
     one = np.ones_like(xg)
     fields = {"rho0": cte_rho0 * one, "T0": cte_T0 * one, "B02": cte_B02 * one,
               "B03": cte_B03 * one}
+    return s, grid, xg, fields
+
+
+def couette_flow_eq(gridpts=51, k2=0.0, k3=1.0, cte_rho0=1.0, cte_T0=1.0, cte_v02=0.0, cte_v03=1.0,
+                    viscosity_value=1.0e-3, physics_type="hd", nodes=GAUSS_NODES, **overrides):
+    """Plane Couette flow (flow + viscosity, Cartesian [0, 1]); the reference's HD regression case
+    (tests/regression_tests/test_couette_flow_HD.py:24-50)."""
+    s = Settings(gridpts=gridpts, geometry="Cartesian", k2=k2, k3=k3, physics_type=physics_type,
+                 flow=True, viscosity=True, viscosity_value=viscosity_value, **overrides)
+    grid, xg = _grid(s.geometry, 0.0, 1.0, gridpts, nodes)
+    one = np.ones_like(xg)
+    width = 1.0
+    fields = {"rho0": cte_rho0 * one, "T0": cte_T0 * one,
+              "v02": cte_v02 * xg / width, "dv02": cte_v02 / width * one,
+              "v03": cte_v03 * xg / width, "dv03": cte_v03 / width * one}
     return s, grid, xg, fields
 
 
@@ -267,4 +283,5 @@ EQUILIBRIA = {
     "magnetothermal_instabilities": magnetothermal_eq,
     "kelvin_helmholtz_cd": kelvin_helmholtz_cd_eq,
     "MRI_accretion": mri_accretion_eq,
+    "couette_flow": couette_flow_eq,
 }

@@ -32,6 +32,8 @@ FILES = {
     "magnetothermal_QR": "regression_tests/baseline/BASE_magnetothermal_QR_k2_0_k3_1.dat",
     "kh_cd_SI": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_SI_k2_-1_k3_pi.dat",
     "kh_cd_QR": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_QR_k2_-1_k3_pi.dat",
+    # the reference's hydrodynamic ("hd", 5-variable state vector) regression case
+    "couette_HD_QR": "regression_tests/baseline/BASE_couette_HD_QR_k2_0_k3_1.dat",
     "mri_matrix": "pylbo_tests/utility_files/v2.0.0_mri_matrix.dat",
     # the only stored run with eigenvectors, eigenfunctions AND residuals (rows N1 of the scope table)
     "mri_subset_efs": "pylbo_tests/utility_files/v2.0.0_mri_subset_efs.dat",

@@ -186,6 +186,23 @@ def test_qr_invert_full_spectrum(golden, name, eqf, lo, tol):
         assert np.min(np.abs(w - 0.015020829511236034j)) < 1e-12
 
 
+def test_hd_state_vector_reproduces_the_stored_hd_spectrum(golden):
+    """physics_type = "hd" (5 variables, 10-wide blocks; absent variables skip their terms,
+    mod_matrix_elements.f08:57-59): the reference's stored Couette-flow HD run
+    (BASE_couette_HD_QR_k2_0_k3_1.dat, flow + viscosity) pins the hd assembly and boundary rows."""
+    g = golden("couette_HD_QR")
+    s, grid, xg, fields = _legacy(eq.couette_flow_eq)
+    assert np.abs(xg - g["grid_gauss"]).max() < 1e-14
+    assert np.abs(fields["v03"] - g["eq_v03"]).max() < 1e-14
+    A, B = asm.build_matrices(s, grid, xg, fields)
+    assert (A.n, A.d) == (510, 10)
+    w = solvers.qr_invert(A.to_dense(), B.to_dense())
+    gold = g["eigenvalues"]
+    sel = gold[(np.abs(gold) > 0.01) & (np.abs(gold) < 1e10)]
+    assert len(sel) > 490
+    assert max(np.min(np.abs(w - x)) / abs(x) for x in sel) <= 1e-10
+
+
 # ---- tests/unit_tests/mod_test_solvers_arpack_shift_invert.pf:16-27,86-167
 EXPECTED_10 = np.array([
     -0.7795557649951639 - 0.3190570519782475j, -0.40222728775310573 - 0.1591345610324656j,
