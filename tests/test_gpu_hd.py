@@ -64,7 +64,7 @@ def test_matvec_solve_and_operator(ctx, physics_type):
     assert np.linalg.norm(ctx.apply_op(x) - xl) <= 1e-9 * np.linalg.norm(xl)
 
 
-@pytest.mark.parametrize("physics_type,gridpts,sigma,nev", [("hd", 51, 0.5 - 0.3j, 6), ("hd", 201, 0.5 - 0.3j, 10),
+@pytest.mark.parametrize("physics_type,gridpts,sigma,nev", [("hd", 51, 0.53 - 0.31j, 6), ("hd", 201, 0.53 - 0.31j, 10),
                                                             ("hd-1d", 51, 10.0 + 1.0j, 3)])
 def test_shift_invert_matches_oracle(ctx, physics_type, gridpts, sigma, nev):
     (s, grid, fields), (A, B) = both(physics_type, gridpts)

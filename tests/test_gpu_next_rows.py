@@ -199,7 +199,7 @@ def test_arnoldi_general_pfunit_known_answers(ctx, which, idxs):
     for k in range(4):
         assert np.linalg.norm(ap @ vr[:, k] - omega[k] * (bp @ vr[:, k])) < 1e-10
     # the factors of B are not left behind as if they were those of A - sigma B
-    with pytest.raises(lb.LegolasError):
+    with pytest.raises(lb.LgpuError):
         ctx.solve(np.ones(n, dtype=complex))
 
 
