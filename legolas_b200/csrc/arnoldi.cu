@@ -229,10 +229,14 @@ struct CgsArgs {
   cd* hsub;
 };
 
+// Device-wide barrier of the consumer threads (pattern of cooperative groups' grid sync): the CTA
+// barrier orders every consumer's earlier stores before thread 0's fence + arrival, thread 0's
+// acquire load orders the other CTAs' stores before the second CTA barrier.  Data published
+// across the barrier is read with ld.global.cg (L2), never through L1.
 __device__ __forceinline__ void cgs_grid_barrier(unsigned long long* ctr, unsigned long long target) {
-  __threadfence();
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (threadIdx.x == 0) {
+    __threadfence();
     atomicAdd(ctr, 1ULL);
     unsigned long long v;
     do {
@@ -240,7 +244,6 @@ __device__ __forceinline__ void cgs_grid_barrier(unsigned long long* ctr, unsign
     } while (v < target);
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
-  __threadfence();
 }
 
 __device__ __forceinline__ cd ldcg_cd(const cd* p) {
@@ -248,15 +251,27 @@ __device__ __forceinline__ cd ldcg_cd(const cd* p) {
   return cd{v.x, v.y};
 }
 
-// every CTA: hs[c] = sum over CTAs of partial[b][c], fixed order (consumer warps, one column each)
-__device__ __forceinline__ void cgs_sum_partials(const cd* partial, int ncols, cd* hs, int warp, int lane) {
-  for (int c = warp; c < ncols; c += 8) {
-    cd s{0.0, 0.0};
-    for (unsigned int b = lane; b < gridDim.x; b += 32) s += ldcg_cd(partial + static_cast<size_t>(b) * PSTRIDE + c);
-    s.x = warp_sum(s.x);
-    s.y = warp_sum(s.y);
-    if (lane == 0) hs[c] = s;
+// every CTA: hs[c] = sum over CTAs of partial[b][c] in one fixed order.  Thread (c, g) of the 64 x 4
+// consumer threads adds the partials of CTAs g, g + 4, ... : all its loads are independent and in
+// flight together (one L2 round trip instead of one per partial), consecutive threads read
+// consecutive columns of one CTA's row; the four group sums are combined through shared memory.
+constexpr int CGS_MAX_GRID = 160;   // CTAs of the fused step kernel (one per SM)
+__device__ __forceinline__ void cgs_sum_partials(const cd* partial, int ncols, cd* hs, cd* scratch, int tid) {
+  const int c = tid & 63, g = tid >> 6;
+  const int nb = static_cast<int>(gridDim.x);
+  constexpr int PER = CGS_MAX_GRID / PASS_GROUPS;
+  cd x[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int b = g + PASS_GROUPS * k;
+    x[k] = (c < ncols && b < nb) ? ldcg_cd(partial + static_cast<size_t>(b) * PSTRIDE + c) : cd{0.0, 0.0};
   }
+  cd s0{0.0, 0.0}, s1{0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < PER; k += 2) { s0 += x[k]; s1 += x[k + 1]; }
+  scratch[g * 64 + c] = s0 + s1;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid < ncols) hs[tid] = (scratch[tid] + scratch[64 + tid]) + (scratch[128 + tid] + scratch[192 + tid]);
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   }
   publish_dots(partial1);
   cgs_grid_barrier(a.gbar, a.bar_base + gridDim.x);
-  cgs_sum_partials(partial1, ncols, hs, warp, lane);
+  cgs_sum_partials(partial1, ncols, hs, part, tid);
   if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = hs[c];
 
   // ---- pass 2: w -= V h ; s = V^H w
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   }
   publish_dots(partial2);
   cgs_grid_barrier(a.gbar, a.bar_base + 2ull * gridDim.x);
-  cgs_sum_partials(partial2, ncols, hs, warp, lane);
+  cgs_sum_partials(partial2, ncols, hs, part, tid);
   if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = a.Hcol[c] + hs[c];
 
   // ---- pass 3: w -= V s ; || w ||
@@ -422,8 +437,15 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   if (tid == 0) partial3[static_cast<size_t>(blockIdx.x) * PSTRIDE] = cd{red[0] + red[1], 0.0};
   cgs_grid_barrier(a.gbar, a.bar_base + 3ull * gridDim.x);
   if (warp == 0) {
+    double x[CGS_MAX_GRID / 32];
+#pragma unroll
+    for (int k = 0; k < CGS_MAX_GRID / 32; ++k) {
+      const unsigned int b = lane + 32 * k;
+      x[k] = b < gridDim.x ? ldcg_cd(partial3 + static_cast<size_t>(b) * PSTRIDE).x : 0.0;
+    }
     double s = 0.0;
-    for (unsigned int b = lane; b < gridDim.x; b += 32) s += ldcg_cd(partial3 + static_cast<size_t>(b) * PSTRIDE).x;
+#pragma unroll
+    for (int k = 0; k < CGS_MAX_GRID / 32; ++k) s += x[k];
     s = warp_sum(s);
     if (lane == 0) s_norm = sqrt(s);
   }
@@ -683,7 +705,7 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   const int tiles_max = (L.ntiles + grid - 1) / grid;
   int nstages = 5;
   while (nstages > 2 && cgs2_smem(ncols, nstages, tiles_max) > 210 * 1024) --nstages;
-  if (!enabled || ncols < 1 || ncols > KRYLOV_PASS_MAXCOL || work.gbar == nullptr ||
+  if (!enabled || ncols < 1 || ncols > KRYLOV_PASS_MAXCOL || work.gbar == nullptr || grid > CGS_MAX_GRID ||
       cgs2_smem(ncols, nstages, tiles_max) > 210 * 1024)
     return false;
   static bool configured = false;
