@@ -13,15 +13,107 @@
 #include <limits>
 #include <vector>
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define LGPU_DENSE_AVX2 1
+#endif
+
 namespace lgpu {
 namespace dense {
 
 using cplx = std::complex<double>;
 
+// ---- plane rotations on rows / columns of a column-major matrix -------------------------------
+// rot_rows:  [x_j ; y_j] <- [c s ; -conj(s) c] [x_j ; y_j]  for the row pair (x, y) = rows (i, i+1),
+//            columns j0 .. j1-1 (p points at (i, j0); the two rows are adjacent in memory)
+// rot_cols:  [a_j b_j] <- [a_j b_j] [c -s ; conj(s) c]      for two columns a, b, rows 0 .. m-1
+// The Schur iteration spends its time here (ncv ~ 40: everything is in L1, the loops are bound by
+// instruction count), so on x86-64 with AVX2 + FMA (checked at run time) one 256-bit register
+// holds the row pair of a column, resp. two consecutive rows of a column.
+inline void rot_rows_scalar(cplx* p, int ld, int count, double c, cplx s) {
+  for (int j = 0; j < count; ++j, p += ld) {
+    const cplx x = p[0], y = p[1];
+    p[0] = c * x + s * y;
+    p[1] = -std::conj(s) * x + c * y;
+  }
+}
+inline void rot_cols_scalar(cplx* a, cplx* b, int m, double c, cplx s) {
+  for (int j = 0; j < m; ++j) {
+    const cplx x = a[j], y = b[j];
+    a[j] = c * x + std::conj(s) * y;
+    b[j] = -s * x + c * y;
+  }
+}
+#ifdef LGPU_DENSE_AVX2
+__attribute__((target("avx2,fma"))) inline void rot_rows_avx2(cplx* p, int ld, int count, double c, cplx s) {
+  const __m256d vc = _mm256_set1_pd(c);
+  const __m256d s1 = _mm256_setr_pd(s.real(), s.real(), -s.real(), -s.real());
+  const __m256d s2 = _mm256_setr_pd(-s.imag(), s.imag(), -s.imag(), s.imag());
+  for (int j = 0; j < count; ++j, p += ld) {
+    double* q = reinterpret_cast<double*>(p);
+    const __m256d v = _mm256_loadu_pd(q);                    // [xr xi yr yi]
+    const __m256d sw = _mm256_permute2f128_pd(v, v, 0x01);   // [yr yi xr xi]
+    const __m256d swi = _mm256_permute_pd(sw, 0x5);          // [yi yr xi xr]
+    __m256d r = _mm256_mul_pd(vc, v);
+    r = _mm256_fmadd_pd(s1, sw, r);
+    r = _mm256_fmadd_pd(s2, swi, r);
+    _mm256_storeu_pd(q, r);
+  }
+}
+__attribute__((target("avx2,fma"))) inline void rot_cols_avx2(cplx* a, cplx* b, int m, double c, cplx s) {
+  const __m256d vc = _mm256_set1_pd(c), sr = _mm256_set1_pd(s.real());
+  const __m256d si = _mm256_setr_pd(s.imag(), -s.imag(), s.imag(), -s.imag());
+  double* pa = reinterpret_cast<double*>(a);
+  double* pb = reinterpret_cast<double*>(b);
+  int j = 0;
+  for (; j + 2 <= m; j += 2) {
+    const __m256d x = _mm256_loadu_pd(pa + 2 * j), y = _mm256_loadu_pd(pb + 2 * j);
+    const __m256d xs = _mm256_permute_pd(x, 0x5), ys = _mm256_permute_pd(y, 0x5);   // re <-> im
+    __m256d t = _mm256_mul_pd(vc, x);
+    t = _mm256_fmadd_pd(sr, y, t);
+    t = _mm256_fmadd_pd(si, ys, t);
+    __m256d u = _mm256_mul_pd(vc, y);
+    u = _mm256_fnmadd_pd(sr, x, u);
+    u = _mm256_fmadd_pd(si, xs, u);
+    _mm256_storeu_pd(pa + 2 * j, t);
+    _mm256_storeu_pd(pb + 2 * j, u);
+  }
+  if (j < m) rot_cols_scalar(a + j, b + j, m - j, c, s);
+}
+inline bool have_avx2() {
+  static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+  return ok;
+}
+#endif
+inline void rot_rows(cplx* p, int ld, int count, double c, cplx s) {
+#ifdef LGPU_DENSE_AVX2
+  if (have_avx2()) return rot_rows_avx2(p, ld, count, c, s);
+#endif
+  rot_rows_scalar(p, ld, count, c, s);
+}
+inline void rot_cols(cplx* a, cplx* b, int m, double c, cplx s) {
+#ifdef LGPU_DENSE_AVX2
+  if (have_avx2()) return rot_cols_avx2(a, b, m, c, s);
+#endif
+  rot_cols_scalar(a, b, m, c, s);
+}
+
 inline double cabs1(cplx z) { return std::fabs(z.real()) + std::fabs(z.imag()); }
 
 // Plane rotation [c s; -conj(s) c] [f; g] = [r; 0] with real c (zlartg).
 inline void lartg(cplx f, cplx g, double* c, cplx* s, cplx* r) {
+  {
+    // both entries comfortably inside the range where squares neither overflow nor underflow
+    // (the unscaled branch of LAPACK 3.10's zlartg): no hypot, two square roots
+    const double f2 = std::norm(f), g2 = std::norm(g);
+    if (f2 > 1e-140 && f2 < 1e140 && g2 > 1e-140 && g2 < 1e140) {
+      const double h2 = f2 + g2;
+      *c = std::sqrt(f2 / h2);
+      *r = f / *c;
+      *s = std::conj(g) * (f / std::sqrt(f2 * h2));
+      return;
+    }
+  }
   const double g1 = std::abs(g);
   if (g1 == 0.0) {
     *c = 1.0; *s = 0.0; *r = f;
@@ -105,22 +197,9 @@ inline int hessenberg_schur(int n, cplx* H, int ldh, cplx* Z, int ldz, int nz, c
       double c; cplx s, r;
       lartg(x, y, &c, &s, &r);
       if (k > l) { h(k, k - 1) = r; h(k + 1, k - 1) = 0.0; }
-      for (int j = k; j < n; ++j) {
-        const cplx t = c * h(k, j) + s * h(k + 1, j);
-        h(k + 1, j) = -std::conj(s) * h(k, j) + c * h(k + 1, j);
-        h(k, j) = t;
-      }
-      const int jmax = std::min(k + 2, ihi);
-      for (int j = 0; j <= jmax; ++j) {
-        const cplx t = c * h(j, k) + std::conj(s) * h(j, k + 1);
-        h(j, k + 1) = -s * h(j, k) + c * h(j, k + 1);
-        h(j, k) = t;
-      }
-      for (int j = 0; j < nz; ++j) {
-        const cplx t = c * z(j, k) + std::conj(s) * z(j, k + 1);
-        z(j, k + 1) = -s * z(j, k) + c * z(j, k + 1);
-        z(j, k) = t;
-      }
+      rot_rows(&h(k, k), ldh, n - k, c, s);
+      rot_cols(&h(0, k), &h(0, k + 1), std::min(k + 2, ihi) + 1, c, s);
+      rot_cols(&z(0, k), &z(0, k + 1), nz, c, s);
       if (k + 1 < ihi) { x = h(k + 1, k); y = h(k + 2, k); }
     }
   }

@@ -246,21 +246,9 @@ class Iram {
             double c; cplx s, r;
             dense::lartg(f, g, &c, &s, &r);
             if (i > istart) { h(i, i - 1, ld) = r; h(i + 1, i - 1, ld) = 0.0; }
-            for (int j = i; j < kplusp; ++j) {
-              const cplx t = c * h(i, j, ld) + s * h(i + 1, j, ld);
-              h(i + 1, j, ld) = -std::conj(s) * h(i, j, ld) + c * h(i + 1, j, ld);
-              h(i, j, ld) = t;
-            }
-            for (int j = 0; j <= std::min(i + 2, iend); ++j) {
-              const cplx t = c * h(j, i, ld) + std::conj(s) * h(j, i + 1, ld);
-              h(j, i + 1, ld) = -s * h(j, i, ld) + c * h(j, i + 1, ld);
-              h(j, i, ld) = t;
-            }
-            for (int j = 0; j <= std::min(i + jj + 1, kplusp - 1); ++j) {
-              const cplx t = c * q(j, i) + std::conj(s) * q(j, i + 1);
-              q(j, i + 1) = -s * q(j, i) + c * q(j, i + 1);
-              q(j, i) = t;
-            }
+            dense::rot_rows(&h(i, i, ld), ld, kplusp - i, c, s);
+            dense::rot_cols(&h(0, i, ld), &h(0, i + 1, ld), std::min(i + 2, iend) + 1, c, s);
+            dense::rot_cols(&q(0, i), &q(0, i + 1), std::min(i + jj + 1, kplusp - 1) + 1, c, s);
             if (i < iend - 1) { f = h(i + 1, i, ld); g = h(i + 2, i, ld); }
           }
         }
