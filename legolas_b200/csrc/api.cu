@@ -359,8 +359,8 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
   c->factor_of_B = of_B;
   if (of_B) sigma = cd{0.0, 0.0};
   if (c->splan.n != c->G) {
-    c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 3),
-                             env_int("LGPU_SLU_TOP", 32));
+    c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 2),
+                             env_int("LGPU_SLU_TOP", 8));
     c->pairs.ensure(std::max<size_t>(c->splan.pair_records, 1) * PAIR_STRIDE);
     c->topfac.ensure(TOP_STRIDE);
     c->fwork.ensure(c->splan.work_rows * ROW_STRIDE);
@@ -553,6 +553,9 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   const int ncv = cfg->ncv, nev = cfg->nev;
   c->basis = make_basis_layout(n, ncv);
   c->V.ensure(c->basis.elems());
+  // the fused Gram-Schmidt kernels stream whole groups of four columns and all 64 rows of the last
+  // tile: entries outside the current basis must be finite (they meet zero coefficients)
+  CUDA_CHECK(cudaMemsetAsync(c->V.p, 0, sizeof(cd) * c->basis.elems(), c->stream));
   c->vcur.ensure(n);
   c->resid.ensure(n);
   c->Hdev.ensure(static_cast<size_t>(ncv) * ncv);

@@ -275,11 +275,19 @@ __device__ __forceinline__ void cgs_sum_partials(const cd* partial, int ncols, c
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
+// CPG > 0: the basis has exactly 4 * CPG columns in play as far as the loops are concerned (columns
+// ncols .. 4 * CPG - 1 are stale but finite data of the basis, their coefficients are zero and
+// their projections are never published): no per-column predicates in the tile loops.
+// CPG == 0: any ncols <= KRYLOV_PASS_MAXCOL, predicated.
+template <int CPG>
 __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __grid_constant__ CgsArgs a) {
+  constexpr bool EXACT = CPG > 0;
+  constexpr int NJ = EXACT ? CPG : PASS_CPG;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const BasisLayout& L = a.L;
   const int ncols = a.ncols, nstages = a.nstages;
-  const int sstride = (ncols + 1) * PASS_T;
+  const int ncopy = EXACT ? PASS_GROUPS * CPG : ncols;   // columns a stage holds
+  const int sstride = (ncopy + 1) * PASS_T;
   cd* buf = reinterpret_cast<cd*>(smem_raw);                            // [nstages][sstride]
   cd* wkeep = buf + static_cast<size_t>(nstages) * sstride;              // [tiles_max][64]
   cd* part = wkeep + static_cast<size_t>(a.tiles_max) * PASS_T;          // [2][4][64]
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncols * PASS_T);
+      const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncopy * PASS_T);
       for (int u = 0; u < 3 * nt; ++u) {
         const int t = t0 + u % nt;
         if (u >= nstages) mbar_wait(&empty[stage], phase ^ 1u);
@@ -312,31 +320,41 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         const uint32_t wbytes = u < nt ? static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T)) : 0u;
         mbar_expect_tx(&full[stage], vbytes + wbytes);
         bulk_g2s(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[stage]);
-        if (wbytes) bulk_g2s(sb + ncols * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[stage]);
+        if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[stage]);
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
     return;
   }
   // ---- consumers: 64 rows x 4 column groups
-  const int cpg = (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
+  const int cpg = EXACT ? CPG : (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
   const int r = tid & (PASS_T - 1), q = tid >> 6;
+  if (EXACT) {   // coefficients of the padding columns stay zero for the whole step
+    if (tid < KRYLOV_PASS_MAXCOL) hs[tid] = cd{0.0, 0.0};
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
   int stage = 0;
   uint32_t phase = 0;
   int flip = 0;
-  cd acc[PASS_CPG];
-  cd v[PASS_CPG];
+  cd acc[NJ];
+  cd v[NJ];
   cd* xw = part;   // [8 warps][PASS_CPG] scratch of the row reduction
 
   auto load_tile = [&](int t, bool want_w, cd& wi) {
     const bool valid = t * PASS_T + r < L.n;
     mbar_wait(&full[stage], phase);
     const cd* sb = buf + static_cast<size_t>(stage) * sstride;
-    if (want_w) wi = valid ? sb[ncols * PASS_T + r] : cd{0.0, 0.0};
+    if (want_w) wi = valid ? sb[ncopy * PASS_T + r] : cd{0.0, 0.0};
+    if (EXACT) {   // rows past the end of the basis are zero in memory
+      const cd* col = sb + q * (CPG * PASS_T) + r;
 #pragma unroll
-    for (int j = 0; j < PASS_CPG; ++j) {
-      const int c = q * cpg + j;
-      v[j] = (j < cpg && c < ncols && valid) ? sb[c * PASS_T + r] : cd{0.0, 0.0};
+      for (int j = 0; j < NJ; ++j) v[j] = col[j * PASS_T];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int c = q * cpg + j;
+        v[j] = (j < cpg && c < ncols && valid) ? sb[c * PASS_T + r] : cd{0.0, 0.0};
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);   // the tile now lives in registers
@@ -345,12 +363,20 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   // w_r -= sum_c V(r, c) hs[c] from the registers of the four column groups of row r
   auto correct = [&](int i) -> cd {
     cd p0{0.0, 0.0}, p1{0.0, 0.0};
+    if (EXACT) {
+      const cd* hq = hs + q * CPG;
 #pragma unroll
-    for (int j = 0; j < PASS_CPG; j += 2) {
-      if (j < cpg) {
-        const int c = q * cpg + j;
-        cfma(p0, v[j], hs[min(c, ncols - 1)]);
-        cfma(p1, v[j + 1], hs[min(c + 1, ncols - 1)]);
+      for (int j = 0; j < NJ; ++j) {
+        if (j & 1) cfma(p1, v[j], hq[j]); else cfma(p0, v[j], hq[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NJ; j += 2) {
+        if (j < cpg) {
+          const int c = q * cpg + j;
+          cfma(p0, v[j], hs[min(c, ncols - 1)]);
+          cfma(p1, v[j + 1], hs[min(c + 1, ncols - 1)]);
+        }
       }
     }
     cd* pp = part + flip * PASS_GROUPS * PASS_T;
@@ -362,8 +388,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   };
   auto publish_dots = [&](cd* dst) {   // rows -> one value per (CTA, column)
 #pragma unroll
-    for (int j = 0; j < PASS_CPG; ++j) {
-      if (j < cpg) {
+    for (int j = 0; j < NJ; ++j) {
+      if (EXACT || j < cpg) {
         acc[j].x = warp_sum(acc[j].x);
         acc[j].y = warp_sum(acc[j].y);
       }
@@ -371,7 +397,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < PASS_CPG; ++j) xw[warp * PASS_CPG + j] = acc[j];
+      for (int j = 0; j < NJ; ++j) xw[warp * PASS_CPG + j] = acc[j];
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int e = tid; e < PASS_GROUPS * cpg; e += 256) {
@@ -388,14 +414,14 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
 
   // ---- pass 1: h = V^H w
 #pragma unroll
-  for (int j = 0; j < PASS_CPG; ++j) acc[j] = cd{0.0, 0.0};
+  for (int j = 0; j < NJ; ++j) acc[j] = cd{0.0, 0.0};
   for (int i = 0; i < nt; ++i) {
     cd wi{0.0, 0.0};
     load_tile(t0 + i, true, wi);
     if (q == 0) wkeep[i * PASS_T + r] = wi;
 #pragma unroll
-    for (int j = 0; j < PASS_CPG; ++j)
-      if (j < cpg) cfmac(acc[j], v[j], wi);
+    for (int j = 0; j < NJ; ++j)
+      if (EXACT || j < cpg) cfmac(acc[j], v[j], wi);
   }
   publish_dots(partial1);
   cgs_grid_barrier(a.gbar, a.bar_base + gridDim.x);
@@ -404,15 +430,16 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
 
   // ---- pass 2: w -= V h ; s = V^H w
 #pragma unroll
-  for (int j = 0; j < PASS_CPG; ++j) acc[j] = cd{0.0, 0.0};
+  for (int j = 0; j < NJ; ++j) acc[j] = cd{0.0, 0.0};
   for (int i = 0; i < nt; ++i) {
     cd wi{0.0, 0.0};
     load_tile(t0 + i, false, wi);
     wi = correct(i);
+    if (EXACT && (t0 + i) * PASS_T + r >= L.n) wi = cd{0.0, 0.0};
     if (q == 0) wkeep[i * PASS_T + r] = wi;
 #pragma unroll
-    for (int j = 0; j < PASS_CPG; ++j)
-      if (j < cpg) cfmac(acc[j], v[j], wi);
+    for (int j = 0; j < NJ; ++j)
+      if (EXACT || j < cpg) cfmac(acc[j], v[j], wi);
   }
   publish_dots(partial2);
   cgs_grid_barrier(a.gbar, a.bar_base + 2ull * gridDim.x);
@@ -698,31 +725,50 @@ static size_t cgs2_smem(int ncols, int nstages, int tiles_max) {
                        2 * PASS_GROUPS * PASS_T + KRYLOV_PASS_MAXCOL) + 16 * nstages;
 }
 
+template <int CPG>
+static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  void* args[] = {const_cast<CgsArgs*>(&a)};
+  CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(krylov_cgs2_kernel<CPG>), dim3(grid), dim3(PASS_THREADS),
+                                         args, smem, stream));
+}
+
 bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const KrylovWork& work, cd* Hcol,
                       int newcol, cd* vplain, cd* hsub, cudaStream_t stream, LaunchLog* log) {
   static const bool enabled = [] { const char* e = std::getenv("LGPU_CGS2_FUSED"); return !(e && e[0] == '0'); }();
+  static const bool exact_ok = [] { const char* e = std::getenv("LGPU_CGS2_EXACT"); return !(e && e[0] == '0'); }();
   const int grid = std::max(1, std::min(sm_count(), L.ntiles));
   const int tiles_max = (L.ntiles + grid - 1) / grid;
+  // columns-per-group variants without per-column predicates: they stream 4 * cpg <= ncv columns
+  const int cpg = (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
+  const bool exact = exact_ok && cpg >= 5 && cpg <= 10 && PASS_GROUPS * cpg <= L.ncv;
+  const int ncopy = exact ? PASS_GROUPS * cpg : ncols;
   int nstages = 5;
-  while (nstages > 2 && cgs2_smem(ncols, nstages, tiles_max) > 210 * 1024) --nstages;
+  while (nstages > 2 && cgs2_smem(ncopy, nstages, tiles_max) > 210 * 1024) --nstages;
   if (!enabled || ncols < 1 || ncols > KRYLOV_PASS_MAXCOL || work.gbar == nullptr || grid > CGS_MAX_GRID ||
-      cgs2_smem(ncols, nstages, tiles_max) > 210 * 1024)
+      cgs2_smem(ncopy, nstages, tiles_max) > 210 * 1024)
     return false;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
-  }
   CgsArgs a{};
   a.L = L; a.V = V; a.ncols = ncols; a.nstages = nstages; a.tiles_max = tiles_max; a.w = w;
   a.partial = work.partial; a.Hcol = Hcol; a.scal = work.scal; a.gbar = work.gbar;
   a.bar_base = *work.gbar_count;
   *work.gbar_count += 3ull * grid;
   a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
-  void* args[] = {&a};
+  const size_t smem = cgs2_smem(ncopy, nstages, tiles_max);
   log->begin(LK_CGS2, 16.0 * L.n * (3.0 * ncols + 4.0));
-  CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(krylov_cgs2_kernel), dim3(grid), dim3(PASS_THREADS),
-                                         args, cgs2_smem(ncols, nstages, tiles_max), stream));
+  switch (exact ? cpg : 0) {
+    case 5: launch_cgs2<5>(a, grid, smem, stream); break;
+    case 6: launch_cgs2<6>(a, grid, smem, stream); break;
+    case 7: launch_cgs2<7>(a, grid, smem, stream); break;
+    case 8: launch_cgs2<8>(a, grid, smem, stream); break;
+    case 9: launch_cgs2<9>(a, grid, smem, stream); break;
+    case 10: launch_cgs2<10>(a, grid, smem, stream); break;
+    default: launch_cgs2<0>(a, grid, smem, stream); break;
+  }
   log->end();
   log->launches += 1;
   return true;

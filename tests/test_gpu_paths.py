@@ -56,9 +56,10 @@ def default_result():
 @pytest.mark.parametrize("env_extra", [
     {"LGPU_SLU_FUSE": "0"},                      # upper solve stages as separate launches
     {"LGPU_CGS2_FUSED": "0"},                    # three Gram-Schmidt pass kernels + scale
+    {"LGPU_CGS2_EXACT": "0"},                    # fused step kernel with per-column predicates only
     {"LGPU_B_ELL": "0"},                         # dense block product for B x
     {"LGPU_GEMM_ROWS": "0"},                     # shared-memory tiled restart GEMM
-    {"LGPU_SLU_MU0": "3", "LGPU_SLU_MU1": "2", "LGPU_SLU_TOP": "8"},   # deeper stage tree
+    {"LGPU_SLU_MU0": "3", "LGPU_SLU_MU1": "3", "LGPU_SLU_TOP": "32"},  # another stage tree
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_matches_default(default_result, env_extra):
     got = run_variant(env_extra)
