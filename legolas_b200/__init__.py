@@ -3,7 +3,8 @@ the shift-invert Arnoldi eigen-solve, behind a C ABI (include/legolas_b200.h).
 
 ``legolas_b200.api`` mirrors the reference's host interface (build_matrices / solve_evp),
 ``legolas_b200.equilibria`` samples the benchmark equilibria on the host,
-``legolas_b200.sweep`` shards independent shifts / wavenumbers over the GPUs of one node.
+``legolas_b200.sweep`` shards independent shifts / wavenumbers over the GPUs of one node,
+``legolas_b200.datfile`` writes the reference's datfile from device-resident results.
 """
 from .api import (ArpackConfig, Context, LegolasError, Matrices, Settings, SolverSettings,  # noqa: F401
                   build_matrices, new_arpack_config, solve_evp, zlarnv)

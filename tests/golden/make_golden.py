@@ -68,6 +68,22 @@ def main():
             out["eigenvectors"] = d["eigenvectors"]
         if "residuals" in d:
             out["residuals"] = d["residuals"]
+        if key == "mri_subset_efs":
+            # the raw header of a 2.x datfile (everything before the eigenvalue block), the byte-level
+            # pin of the writer in legolas_b200/datfile.py; plus the header entries the writer is fed
+            from oracle import datfile as odf
+            raw = open(os.path.join(REF, rel), "rb").read()
+            st = odf._Stream(raw)
+            st.s(len("legolas_version")), st.s(10), st.take("ii")
+            odf._read_v2_header(st, {})
+            out["header_bytes"] = np.frombuffer(raw[:st.pos], dtype=np.uint8)
+            out["header_json"] = json.dumps({
+                k: (v if not isinstance(v, complex) else [v.real, v.imag])
+                for k, v in d.items()
+                if k in ("x_start", "x_end", "ef_subset_radius", "ef_subset_center", "solver", "arpack_mode",
+                         "number_of_eigenvalues", "which_eigenvalues", "ncv", "maxiter", "tolerance",
+                         "boundary_type", "physics", "has_matrices", "has_eigenvectors", "has_residuals",
+                         "has_efs", "has_derived_efs", "ef_subset_used")})
         if "matrix_A" in d:
             out["A_rows"], out["A_cols"], out["A_vals"] = d["matrix_A"]
             out["B_rows"], out["B_cols"], out["B_vals"] = d["matrix_B"]

@@ -221,3 +221,34 @@ def test_arnoldi_general_matches_oracle(ctx, name, gridpts, which, nev):
         assert np.min(np.abs(om_o - w)) <= 1e-8 * abs(w)
     res = ctx.residuals(omega, vr)
     assert res.max() < 1e-9
+
+
+# ------------------------------------------------------------------ N2: datfile from the device
+def test_datfile_of_a_device_run_reads_back_like_the_reference_file(ctx, golden, tmp_path):
+    """create_datfile with every device-backed block on (eigenfunctions, residuals, matrices) for the
+    reference's stored MRI run: eigenfunctions equal the stored ones, residuals agree with the
+    stored ones like the oracle's do, the matrix triplets are the oracle's in the same order."""
+    from legolas_b200 import datfile as ldf
+    from oracle.datfile import read_datfile
+    from test_datfile import mri_run
+    g, hdr, s, grid, fields, io, info, _ = mri_run(golden)
+    io.write_matrices = True
+    so, go, xgo, fo = oeq.mri_accretion_eq(gridpts=10, nodes=g["gauss_nodes"])     # the nodes in the file's header
+    so.gauss_nodes, so.gauss_weights = g["gauss_nodes"], g["gauss_weights"]
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    ctx.assemble(s, go, xgo, fo)
+    path = ldf.create_datfile(tmp_path / "mri_gpu.dat", s, go, xgo, fo, g["eigenvalues"], ctx=ctx,
+                              eigenvectors=g["eigenvectors"], io=io, info=info)
+    d = read_datfile(path)
+    assert np.array_equal(d["ef_written_idxs"], g["ef_written_idxs"])
+    for name in d["state_vector"]:
+        ref = g["ef_" + name]
+        assert np.all(np.abs(d["eigenfunctions"][name] - ref) <= 1e-12 * np.abs(ref).max()), name
+    ok = np.isfinite(g["residuals"]) & (g["residuals"] > 0)
+    ratio = d["residuals"][ok] / g["residuals"][ok]
+    assert ok.sum() > 100 and ratio.min() > 0.9 and ratio.max() < 1.1, (ratio.min(), ratio.max())
+    for label, M in (("matrix_A", A), ("matrix_B", B)):
+        r, c, v = M.to_coo()
+        assert np.array_equal(d[label][0], r) and np.array_equal(d[label][1], c), label
+        ref = v if label == "matrix_A" else v.real
+        assert np.all(np.abs(d[label][2] - ref) <= 1e-12 * np.abs(ref) + 1e-15 * np.abs(ref).max()), label
