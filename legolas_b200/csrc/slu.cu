@@ -216,9 +216,15 @@ __device__ __forceinline__ void pair_forward(const Ring& rg, RingPos& pos, const
   const int c0 = warp * CW;
   const cd* g0 = ring_acquire(rg, pos);
   const uint8_t* perm = reinterpret_cast<const uint8_t*>(g0 + PR_PERM);
-  // lanes 0..3 hold the entries of (P s)_1 that multiply this warp's columns
-  const cd v1 = s[perm[c0 + (lane & (CW - 1))]];
-  const cd v2 = s[perm[SB + lane]];
+  // the CW entries of (P s)_1 that multiply this warp's columns: one word of the permutation, then
+  // broadcast reads of the right-hand side (no shuffles on the critical path of the pair)
+  static_assert(CW == 4, "one 32-bit word holds the permutation entries of a warp's columns");
+  const uint32_t pw = *reinterpret_cast<const uint32_t*>(perm + c0);
+  cd v1[CW];
+#pragma unroll
+  for (int c = 0; c < CW; ++c) v1[c] = s[(pw >> (8 * c)) & 0xffu];
+  // (P s)_2 of the row this lane finishes below (lanes 0 .. CW-1)
+  const cd v2row = s[perm[SB + c0 + (lane & (CW - 1))]];
   const cd* L = g0 + PR_L11I;
   cd ga{0.0, 0.0}, gb{0.0, 0.0};
 #pragma unroll
@@ -226,23 +232,22 @@ __device__ __forceinline__ void pair_forward(const Ring& rg, RingPos& pos, const
     const int col = c0 + c;
     const cd ma = lane >= col ? L[tri_lo_off(col) + lane - col] : cd{0.0, 0.0};
     const cd mb = lane >= col + 1 ? L[tri_lo_off(col + 1) + lane - col - 1] : cd{0.0, 0.0};
-    cfma(ga, ma, shfl_cd(v1, c));
-    cfma(gb, mb, shfl_cd(v1, c + 1));
+    cfma(ga, ma, v1[c]);
+    cfma(gb, mb, v1[c + 1]);
   }
   ring_release(rg, pos, lane);
   const cd* M = ring_acquire(rg, pos);
   cd aa{0.0, 0.0}, ab{0.0, 0.0};
 #pragma unroll
   for (int c = 0; c < CW; c += 2) {
-    cfma(aa, M[(c0 + c) * SB + lane], shfl_cd(v1, c));
-    cfma(ab, M[(c0 + c + 1) * SB + lane], shfl_cd(v1, c + 1));
+    cfma(aa, M[(c0 + c) * SB + lane], v1[c]);
+    cfma(ab, M[(c0 + c + 1) * SB + lane], v1[c + 1]);
   }
   ring_release(rg, pos, lane);
   part[warp * SB + lane] = ga + gb;
   part[(NCW + warp) * SB + lane] = aa + ab;
   consumer_sync();
   // warp w finishes rows 4w .. 4w+3: lanes 0-3 the reduced right-hand side, lanes 4-7 g
-  const cd v2row = shfl_cd(v2, c0 + (lane & (CW - 1)));
   if (lane < 2 * CW) {
     const int row = c0 + (lane & (CW - 1));
     const cd* src = part + (lane < CW ? NCW * SB : 0) + row;
