@@ -549,10 +549,16 @@ struct FusedArgs {
   StageArgs st[MAX_FUSED];
 };
 
+// Pattern of cooperative groups' grid sync, one-directional: the CTA barrier orders every consumer
+// thread's earlier global writes before thread 0's fence + arrival; on the waiting side thread 0's
+// acquire load followed by the CTA barrier orders the other CTA's writes before this CTA's reads,
+// which go past L1 (ld.global.cg).
 __device__ __forceinline__ void grid_signal(unsigned long long* ctr) {
-  __threadfence();
   consumer_sync();
-  if (threadIdx.x == 0) atomicAdd(ctr, 1ULL);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1ULL);
+  }
 }
 __device__ __forceinline__ void grid_wait(const unsigned long long* ctr, unsigned long long target) {
   if (threadIdx.x == 0) {
@@ -562,7 +568,6 @@ __device__ __forceinline__ void grid_wait(const unsigned long long* ctr, unsigne
     } while (v < target);
   }
   consumer_sync();
-  __threadfence();
 }
 
 // smem: [ns slots][nu U slots][buf0][buf1][z][part][big 64 x 64 + 64][barriers], sized for cmax
