@@ -106,6 +106,7 @@ struct lgpu_ctx {
   int bell_w = -1;              // longest row of B; -1: not built for the current B
   bool have_grid = false;       // grid_copy matches the resident matrices
   DevBuf<unsigned long long> d_sync;
+  DevBuf<cd> mbox;              // mailboxes of the fused solve stages (slu.cuh)
   unsigned long long solve_epoch = 0;
   bool factorized = false;
   bool factor_of_B = false;     // general mode: the resident factors are those of B, not of A - sigma B
@@ -132,7 +133,7 @@ struct lgpu_ctx {
     SluDevice d{};
     d.A = factor_of_B ? B.p : A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
     d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
-    d.sync = d_sync.p; d.epoch = &solve_epoch; d.padmask = padmask;
+    d.sync = d_sync.p; d.epoch = &solve_epoch; d.padmask = padmask; d.mbox = mbox.p;
     return d;
   }
 };
@@ -369,12 +370,15 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
     c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
     c->d_info.ensure(1);
     c->d_sync.ensure(SLU_SYNC_COUNTERS);
+    c->mbox.ensure(slu_mbox_elems(c->splan));
   }
   ensure_vectors(c);
   c->log.stream = c->stream;
   // the fused solve stages count finished chunks cumulatively from here on
   CUDA_CHECK(cudaMemsetAsync(c->d_sync.p, 0, sizeof(unsigned long long) * SLU_SYNC_COUNTERS, c->stream));
   c->solve_epoch = 0;
+  // every mailbox entry empty (all-ones NaN) before the first solve with these factors
+  CUDA_CHECK(cudaMemsetAsync(c->mbox.p, 0xFF, sizeof(cd) * slu_mbox_elems(c->splan), c->stream));
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
   slu_factorize(c->splan, c->sdev(), sigma, c->stream, &c->log);
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));

@@ -100,6 +100,12 @@ struct StageArgs {
   cd* fout;          // stage output rows (nchunks x 32)
   cd* gvec;
   cd* xv;            // solution, K x 32
+  // mailbox hand-off inside the fused launch (null / 0 elsewhere)
+  int poll_in;       // fin is a mailbox: poll every entry until it is no longer the all-ones NaN
+  cd* fout_clear;    // the other parity's copy of fout: receives the all-ones pattern
+  cd* zbox;          // this solve's copy of the solved super nodes (K x 32), written next to xv
+  cd* zbox_clear;    // the other parity's copy
+  int poll_z;        // boundary unknowns of a chunk come from zbox (polled) instead of xv
 };
 
 // ---- solve kernels ---------------------------------------------------------------------------
@@ -283,6 +289,28 @@ __device__ __forceinline__ size_t unknown_index(const StageArgs& a, int j) {
   return j < a.m0 ? (static_cast<size_t>(j) << a.l0) : static_cast<size_t>(a.K - 1);
 }
 
+// all-ones NaN: never produced by arithmetic (generated NaNs are canonical, propagated ones carry
+// an input's payload, and this pattern is never an input)
+__device__ __forceinline__ cd mbox_empty() {
+  const double e = __longlong_as_double(-1LL);
+  return cd{e, e};
+}
+__device__ __forceinline__ cd mbox_poll(const cd* p) {
+  double x, y;
+  do {
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
+  } while (__double_as_longlong(x) == -1LL || __double_as_longlong(y) == -1LL);
+  return cd{x, y};
+}
+// a solved super node: the solution vector, and the mailbox when other CTAs of the launch wait for it
+__device__ __forceinline__ void publish_node(const StageArgs& a, size_t node, int lane, cd v) {
+  a.xv[node * SB + lane] = v;
+  if (a.zbox != nullptr) {
+    a.zbox_clear[node * SB + lane] = mbox_empty();
+    a.zbox[node * SB + lane] = v;
+  }
+}
+
 // Unit upper triangular solve by one warp: lane i holds r_i and leaves with x_i.  U is packed by
 // columns with rows already divided by their diagonal entry; the diagonal slot holds 1 / U_ii.
 __device__ __forceinline__ cd unit_upper_solve(const cd* U, cd r, int lane) {
@@ -351,7 +379,7 @@ __device__ __forceinline__ void chunk_backward(const StageArgs& a, const Ring& r
         r = unit_upper_solve(ur.slots + mine.slot * ur.stride, r, lane);
         const int qm = 2 * (i0 + warp) * s + s;
         z[qm * SB + lane] = r;
-        a.xv[unknown_index(a, r0 + qm) * SB + lane] = r;
+        publish_node(a, unknown_index(a, r0 + qm), lane, r);
         __syncwarp();
         if (lane == 0) mbar_arrive(&ur.empty[mine.slot]);
       }
@@ -384,10 +412,17 @@ __device__ __forceinline__ void fwd_stage_body(const StageArgs& a, int chunk, co
   const int C = 1 << a.mu;
   const int r0 = chunk * C;
   const int cnt = min(C, a.m0 - r0);
-  for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + static_cast<size_t>(r0) * SB + e);
+  if (a.poll_in) {
+    for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = mbox_poll(a.fin + static_cast<size_t>(r0) * SB + e);
+  } else {
+    for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + static_cast<size_t>(r0) * SB + e);
+  }
   consumer_sync();
   const cd* res = chunk_forward(a, rg, pos, r0, cnt, buf0, buf1, part);
-  if (threadIdx.x < SB) a.fout[static_cast<size_t>(chunk) * SB + threadIdx.x] = res[threadIdx.x];
+  if (threadIdx.x < SB) {
+    if (a.fout_clear != nullptr) a.fout_clear[static_cast<size_t>(chunk) * SB + threadIdx.x] = mbox_empty();
+    a.fout[static_cast<size_t>(chunk) * SB + threadIdx.x] = res[threadIdx.x];
+  }
 }
 
 __device__ __forceinline__ void bwd_stage_body(const StageArgs& a, int chunk, const Ring& rg, RingPos& pos,
@@ -395,9 +430,12 @@ __device__ __forceinline__ void bwd_stage_body(const StageArgs& a, int chunk, co
   const int C = 1 << a.mu;
   const int r0 = chunk * C;
   const int cnt = min(C, a.m0 - r0);
-  if (threadIdx.x < SB) z[threadIdx.x] = ldcg_cd(a.xv + unknown_index(a, r0) * SB + threadIdx.x);
-  else if (threadIdx.x < 2 * SB)
-    z[cnt * SB + threadIdx.x - SB] = ldcg_cd(a.xv + unknown_index(a, r0 + cnt) * SB + threadIdx.x - SB);
+  if (threadIdx.x < 2 * SB) {
+    const int t = threadIdx.x & (SB - 1);
+    const bool right = threadIdx.x >= SB;
+    const size_t idx = unknown_index(a, right ? r0 + cnt : r0) * SB + t;
+    z[(right ? cnt * SB : 0) + t] = a.poll_z ? mbox_poll(a.zbox + idx) : ldcg_cd(a.xv + idx);
+  }
   consumer_sync();
   chunk_backward(a, rg, pos, ur, upos, r0, cnt, z, part);
 }
@@ -414,7 +452,11 @@ __device__ __forceinline__ void top_stage_body(const StageArgs& a, const Ring& r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cnt = a.m0;
   const int TS = a.top_size;
-  for (int e = tid; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + e);
+  if (a.poll_in) {
+    for (int e = tid; e < cnt * SB; e += NCW * 32) buf0[e] = mbox_poll(a.fin + e);
+  } else {
+    for (int e = tid; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + e);
+  }
   consumer_sync();
   const cd* res = buf0;
   if (cnt > 0) res = chunk_forward(a, rg, pos, 0, cnt, buf0, buf1, part);
@@ -471,10 +513,10 @@ __device__ __forceinline__ void top_stage_body(const StageArgs& a, const Ring& r
       }
     }
     z[lane] = y0;
-    a.xv[lane] = y0;
+    publish_node(a, 0, lane, y0);
     if (TS == 64) {
       z[cnt * SB + lane] = y1;
-      a.xv[static_cast<size_t>(a.K - 1) * SB + lane] = y1;
+      publish_node(a, static_cast<size_t>(a.K - 1), lane, y1);
     }
   }
   consumer_sync();
@@ -536,10 +578,12 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
 
 // The narrow upper stages and the top system in ONE cooperative launch (grid = chunks of the first
 // fused stage, all co-resident): their data is a few MB, their cost is the dependency chain,
-// and a kernel boundary per stage (launch gap, ring start-up) would double it.  CTAs meet through
-// monotonic device counters: stage s forward done (sync[s]) and backward done
-// (sync[MAX_FUSED + s]) count finished chunks over all solves since the factorisation; solve
-// number `epoch` waits for epoch * chunks.  The producer warp never waits on them (the factor
+// and a kernel boundary per stage (launch gap, ring start-up) would double it.  CTAs hand rows up
+// and unknowns down through mailboxes (SluDevice::mbox): a consumer polls the VALUE it needs until
+// it is no longer the all-ones NaN, so a hand-off costs one store and one load round trip and a
+// chunk waits for its own inputs only (the first version counted finished chunks of a whole
+// stage with fence + atomic on one side and poll + barrier + load on the other: ~2.5 k cycles per
+// hand-off, eight of them on the critical path).  The producer warp never waits (the factor
 // records are static), so the next stage's records are on chip when its dependencies arrive.
 struct FusedArgs {
   int nst;                       // fused stages; the last one is the top stage
@@ -548,27 +592,6 @@ struct FusedArgs {
   unsigned long long* sync;      // 2 * MAX_FUSED counters
   StageArgs st[MAX_FUSED];
 };
-
-// Pattern of cooperative groups' grid sync, one-directional: the CTA barrier orders every consumer
-// thread's earlier global writes before thread 0's fence + arrival; on the waiting side thread 0's
-// acquire load followed by the CTA barrier orders the other CTA's writes before this CTA's reads,
-// which go past L1 (ld.global.cg).
-__device__ __forceinline__ void grid_signal(unsigned long long* ctr) {
-  consumer_sync();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1ULL);
-  }
-}
-__device__ __forceinline__ void grid_wait(const unsigned long long* ctr, unsigned long long target) {
-  if (threadIdx.x == 0) {
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
-    } while (v < target);
-  }
-  consumer_sync();
-}
 
 // smem: [ns slots][nu U slots][buf0][buf1][z][part][big 64 x 64 + 64][barriers], sized for cmax
 __global__ void __launch_bounds__(RING_THREADS) slu_fused_stage_kernel(const __grid_constant__ FusedArgs f) {
@@ -614,21 +637,18 @@ __global__ void __launch_bounds__(RING_THREADS) slu_fused_stage_kernel(const __g
   for (int s = 0; s < top; ++s) {
     const StageArgs& a = f.st[s];
     if (b >= a.nchunks) continue;
-    if (s > 0) grid_wait(f.sync + s - 1, f.epoch * f.st[s - 1].nchunks);
-    fwd_stage_body(a, b, rg, pos, buf0, buf1, part);
-    grid_signal(f.sync + s);
+    fwd_stage_body(a, b, rg, pos, buf0, buf1, part);   // inputs of stages > 0: polled from the mailbox
+    consumer_sync();                                   // buf0 / buf1 are reused by the next stage
   }
   if (b == 0) {
-    if (top > 0) grid_wait(f.sync + top - 1, f.epoch * f.st[top - 1].nchunks);
     top_stage_body(f.st[top], rg, pos, ur, upos, buf0, buf1, z, part, big);
-    grid_signal(f.sync + MAX_FUSED + top);
+    consumer_sync();
   }
   for (int s = top - 1; s >= 0; --s) {
     const StageArgs& a = f.st[s];
     if (b >= a.nchunks) continue;
-    grid_wait(f.sync + MAX_FUSED + s + 1, f.epoch * (s + 1 == top ? 1 : f.st[s + 1].nchunks));
-    bwd_stage_body(a, b, rg, pos, ur, upos, z, part);
-    grid_signal(f.sync + MAX_FUSED + s);
+    bwd_stage_body(a, b, rg, pos, ur, upos, z, part);  // boundary unknowns: polled from the mailbox
+    consumer_sync();
   }
 }
 
@@ -1211,8 +1231,25 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     f.nst = ns - sf;
     f.cmax = 1;
     int mu_max = 0;
+    const unsigned long long parity = (*d.epoch + 1) & 1ull;   // of the solve being launched
+    const size_t half = slu_mbox_half(plan);
+    cd* box = d.mbox + parity * half;
+    cd* box_other = d.mbox + (1 - parity) * half;
+    const size_t zoff = plan.rhs_vecs * SB;
     for (int s = sf; s < ns; ++s) {
-      f.st[s - sf] = make_stage_args(plan, d, s, b, xv);
+      StageArgs& a = f.st[s - sf];
+      a = make_stage_args(plan, d, s, b, xv);
+      if (s > sf) {            // input rows come from another CTA of this launch
+        a.fin = box + plan.stages[s].off_fin * SB;
+        a.poll_in = 1;
+      }
+      if (s < ns - 1) {        // output rows go to another CTA of this launch
+        a.fout = box + plan.stages[s + 1].off_fin * SB;
+        a.fout_clear = box_other + plan.stages[s + 1].off_fin * SB;
+        a.poll_z = 1;          // ... and its boundary unknowns come from one
+      }
+      a.zbox = box + zoff;
+      a.zbox_clear = box_other + zoff;
       mu_max = std::max(mu_max, plan.stages[s].mu);
       if (s < ns - 1) top_bytes += stage_algo_bytes(plan, s, 24064.0);
     }
