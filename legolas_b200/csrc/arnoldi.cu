@@ -410,7 +410,6 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
 
   cd* partial1 = a.partial;
   cd* partial2 = a.partial + static_cast<size_t>(gridDim.x) * PSTRIDE;
-  cd* partial3 = a.partial + static_cast<size_t>(2 * gridDim.x) * PSTRIDE;
 
   // ---- pass 1: h = V^H w
 #pragma unroll
@@ -428,53 +427,46 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   cgs_sum_partials(partial1, ncols, hs, part, tid);
   if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = hs[c];
 
-  // ---- pass 2: w -= V h ; s = V^H w
+  // ---- pass 2: w -= V h ; s = V^H w ; || w ||^2
+  double nrm = 0.0;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) acc[j] = cd{0.0, 0.0};
   for (int i = 0; i < nt; ++i) {
     cd wi{0.0, 0.0};
     load_tile(t0 + i, false, wi);
     wi = correct(i);
-    if (EXACT && (t0 + i) * PASS_T + r >= L.n) wi = cd{0.0, 0.0};
-    if (q == 0) wkeep[i * PASS_T + r] = wi;
+    if ((t0 + i) * PASS_T + r >= L.n) wi = cd{0.0, 0.0};
+    if (q == 0) { wkeep[i * PASS_T + r] = wi; nrm += abs2(wi); }
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
       if (EXACT || j < cpg) cfmac(acc[j], v[j], wi);
   }
   publish_dots(partial2);
-  cgs_grid_barrier(a.gbar, a.bar_base + 2ull * gridDim.x);
-  cgs_sum_partials(partial2, ncols, hs, part, tid);
-  if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = a.Hcol[c] + hs[c];
-
-  // ---- pass 3: w -= V s ; || w ||
-  double nrm = 0.0;
-  for (int i = 0; i < nt; ++i) {
-    cd wi{0.0, 0.0};
-    load_tile(t0 + i, false, wi);
-    wi = correct(i);
-    if (q == 0) {
-      wkeep[i * PASS_T + r] = wi;
-      const int gi = (t0 + i) * PASS_T + r;
-      if (gi < L.n) { a.w[gi] = wi; nrm += abs2(wi); }
-    }
-  }
   nrm = warp_sum(nrm);
   if (lane == 0) red[warp] = nrm;
   asm volatile("bar.sync 1, 256;" ::: "memory");
-  if (tid == 0) partial3[static_cast<size_t>(blockIdx.x) * PSTRIDE] = cd{red[0] + red[1], 0.0};
-  cgs_grid_barrier(a.gbar, a.bar_base + 3ull * gridDim.x);
+  if (tid == 0) partial2[static_cast<size_t>(blockIdx.x) * PSTRIDE + KRYLOV_MAXCOL] = cd{red[0] + red[1], 0.0};
+  cgs_grid_barrier(a.gbar, a.bar_base + 2ull * gridDim.x);
+  cgs_sum_partials(partial2, ncols, hs, part, tid);
+  if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = a.Hcol[c] + hs[c];
+  // The norm of the final residual without a third device-wide round: the basis is orthonormal,
+  // so || w - V s ||^2 = || w ||^2 - || s ||^2, and after the first correction || s || is at
+  // rounding level of || w || (no cancellation).  Every CTA evaluates it in the same order.
   if (warp == 0) {
     double x[CGS_MAX_GRID / 32];
 #pragma unroll
     for (int k = 0; k < CGS_MAX_GRID / 32; ++k) {
       const unsigned int b = lane + 32 * k;
-      x[k] = b < gridDim.x ? ldcg_cd(partial3 + static_cast<size_t>(b) * PSTRIDE).x : 0.0;
+      x[k] = b < gridDim.x ? ldcg_cd(partial2 + static_cast<size_t>(b) * PSTRIDE + KRYLOV_MAXCOL).x : 0.0;
     }
-    double s = 0.0;
+    double wn2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < CGS_MAX_GRID / 32; ++k) s += x[k];
-    s = warp_sum(s);
-    if (lane == 0) s_norm = sqrt(s);
+    for (int k = 0; k < CGS_MAX_GRID / 32; ++k) wn2 += x[k];
+    wn2 = warp_sum(wn2);
+    double ss = 0.0;
+    for (int c = lane; c < ncols; c += 32) ss += abs2(hs[c]);
+    ss = warp_sum(ss);
+    if (lane == 0) s_norm = sqrt(fmax(wn2 - ss, 0.0));
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
   const double rnorm = s_norm;
@@ -482,16 +474,22 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     a.scal[0] = rnorm;
     if (a.newcol >= 0 && a.hsub) *a.hsub = cd{rnorm, 0.0};
   }
-  // ---- the next basis vector: V(:, newcol) = vplain = w / ||w||
-  if (a.newcol >= 0) {
-    const double inv = 1.0 / rnorm;
-    for (int e = tid; e < nt * PASS_T; e += 256) {
-      const int i = e >> 6, rr = e & (PASS_T - 1);
-      const int gi = (t0 + i) * PASS_T + rr;
+
+  // ---- pass 3: w -= V s, and the next basis vector V(:, newcol) = vplain = w / ||w|| on the way
+  const double inv = 1.0 / rnorm;
+  for (int i = 0; i < nt; ++i) {
+    cd wi{0.0, 0.0};
+    load_tile(t0 + i, false, wi);
+    wi = correct(i);
+    if (q == 0) {
+      const int gi = (t0 + i) * PASS_T + r;
       if (gi < L.n) {
-        const cd x = wkeep[e] * inv;
-        a.V[(static_cast<size_t>(t0 + i) * L.ncv + a.newcol) * PASS_T + rr] = x;
-        a.vplain[gi] = x;
+        a.w[gi] = wi;
+        if (a.newcol >= 0) {
+          const cd x = wi * inv;
+          a.V[(static_cast<size_t>(t0 + i) * L.ncv + a.newcol) * PASS_T + r] = x;
+          a.vplain[gi] = x;
+        }
       }
     }
   }
@@ -756,7 +754,7 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   a.L = L; a.V = V; a.ncols = ncols; a.nstages = nstages; a.tiles_max = tiles_max; a.w = w;
   a.partial = work.partial; a.Hcol = Hcol; a.scal = work.scal; a.gbar = work.gbar;
   a.bar_base = *work.gbar_count;
-  *work.gbar_count += 3ull * grid;
+  *work.gbar_count += 2ull * grid;
   a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
   const size_t smem = cgs2_smem(ncopy, nstages, tiles_max);
   log->begin(LK_CGS2, 16.0 * L.n * (3.0 * ncols + 4.0));
