@@ -279,6 +279,17 @@ __device__ __forceinline__ void cgs_sum_partials(const cd* partial, int ncols, c
 // ncols .. 4 * CPG - 1 are stale but finite data of the basis, their coefficients are zero and
 // their projections are never published): no per-column predicates in the tile loops.
 // CPG == 0: any ncols <= KRYLOV_PASS_MAXCOL, predicated.
+// How many times slot i % S has been filled before local tile i is streamed in pass `pass` of the
+// fused step (passes run up, down, up over the nt tiles of a CTA; the S tiles a pass ends with stay
+// in their slots for the next pass).  Its parity is the phase of the slot's "full" barrier.
+__device__ __forceinline__ int cgs_fill_number(int pass, int i, int nt, int S) {
+  const int sg = i % S;
+  const int n = (nt - sg + S - 1) / S;        // tiles of this CTA that map to the slot
+  if (pass == 1) return i / S;
+  if (pass == 2) return n + (sg + (n - 1) * S - S - i) / S;   // below the slot's resident tile, downwards
+  return 2 * n - 1 + i / S - 1;               // pass 3: above the slot's resident tile, upwards
+}
+
 template <int CPG>
 __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __grid_constant__ CgsArgs a) {
   constexpr bool EXACT = CPG > 0;
@@ -307,22 +318,26 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   }
   __syncthreads();
   if (warp == 8) {
-    // ---- producer (one lane): three passes over the CTA's tiles through one ring; only the
-    // first pass needs w from global memory
+    // ---- producer (one lane).  Local tile i always lives in ring slot i % S, and the passes run
+    // over the CTA's tiles in alternating directions (up, down, up): the last S tiles of a pass are
+    // the first S of the next one and are still in their slots, so they are neither released nor
+    // streamed again (S / nt of the traffic of passes 2 and 3).  Fill number F of a slot waits for
+    // release F - 1 of that slot; only the first pass needs w from global memory.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      const int S = nstages;
       const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncopy * PASS_T);
-      for (int u = 0; u < 3 * nt; ++u) {
-        const int t = t0 + u % nt;
-        if (u >= nstages) mbar_wait(&empty[stage], phase ^ 1u);
-        cd* sb = buf + static_cast<size_t>(stage) * sstride;
-        const uint32_t wbytes = u < nt ? static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T)) : 0u;
-        mbar_expect_tx(&full[stage], vbytes + wbytes);
-        bulk_g2s(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[stage]);
-        if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[stage]);
-        if (++stage == nstages) { stage = 0; phase ^= 1u; }
-      }
+      auto fill = [&](int i, int F, bool with_w) {
+        const int sg = i % S, t = t0 + i;
+        if (F >= 1) mbar_wait(&empty[sg], static_cast<uint32_t>((F - 1) & 1));
+        cd* sb = buf + static_cast<size_t>(sg) * sstride;
+        const uint32_t wbytes = with_w ? static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T)) : 0u;
+        mbar_expect_tx(&full[sg], vbytes + wbytes);
+        bulk_g2s(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[sg]);
+        if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[sg]);
+      };
+      for (int i = 0; i < nt; ++i) fill(i, cgs_fill_number(1, i, nt, S), true);
+      for (int i = nt - S - 1; i >= 0; --i) fill(i, cgs_fill_number(2, i, nt, S), false);
+      for (int i = S; i < nt; ++i) fill(i, cgs_fill_number(3, i, nt, S), false);
     }
     return;
   }
@@ -333,17 +348,18 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     if (tid < KRYLOV_PASS_MAXCOL) hs[tid] = cd{0.0, 0.0};
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
-  int stage = 0;
-  uint32_t phase = 0;
   int flip = 0;
   cd acc[NJ];
   cd v[NJ];
   cd* xw = part;   // [8 warps][PASS_CPG] scratch of the row reduction
 
-  auto load_tile = [&](int t, bool want_w, cd& wi) {
-    const bool valid = t * PASS_T + r < L.n;
-    mbar_wait(&full[stage], phase);
-    const cd* sb = buf + static_cast<size_t>(stage) * sstride;
+  // local tile i of pass `pass` -> registers (see the producer for the slot / residency rules)
+  auto load_tile = [&](int pass, int i, bool want_w, cd& wi) {
+    const int S = nstages, sg = i % S;
+    const bool valid = (t0 + i) * PASS_T + r < L.n;
+    const bool resident = (pass == 2 && i >= nt - S) || (pass == 3 && i < S);
+    if (!resident) mbar_wait(&full[sg], static_cast<uint32_t>(cgs_fill_number(pass, i, nt, S) & 1));
+    const cd* sb = buf + static_cast<size_t>(sg) * sstride;
     if (want_w) wi = valid ? sb[ncopy * PASS_T + r] : cd{0.0, 0.0};
     if (EXACT) {   // rows past the end of the basis are zero in memory
       const cd* col = sb + q * (CPG * PASS_T) + r;
@@ -356,9 +372,10 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         v[j] = (j < cpg && c < ncols && valid) ? sb[c * PASS_T + r] : cd{0.0, 0.0};
       }
     }
+    // the tile now lives in registers: release the slot unless the next pass starts with it
+    const bool keep = (pass == 1 && i >= nt - S) || (pass == 2 && i < S);
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);   // the tile now lives in registers
-    if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    if (!keep && lane == 0) mbar_arrive(&empty[sg]);
   };
   // w_r -= sum_c V(r, c) hs[c] from the registers of the four column groups of row r
   auto correct = [&](int i) -> cd {
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   for (int j = 0; j < NJ; ++j) acc[j] = cd{0.0, 0.0};
   for (int i = 0; i < nt; ++i) {
     cd wi{0.0, 0.0};
-    load_tile(t0 + i, true, wi);
+    load_tile(1, i, true, wi);
     if (q == 0) wkeep[i * PASS_T + r] = wi;
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
@@ -431,9 +448,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   double nrm = 0.0;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) acc[j] = cd{0.0, 0.0};
-  for (int i = 0; i < nt; ++i) {
+  for (int i = nt - 1; i >= 0; --i) {
     cd wi{0.0, 0.0};
-    load_tile(t0 + i, false, wi);
+    load_tile(2, i, false, wi);
     wi = correct(i);
     if ((t0 + i) * PASS_T + r >= L.n) wi = cd{0.0, 0.0};
     if (q == 0) { wkeep[i * PASS_T + r] = wi; nrm += abs2(wi); }
@@ -479,7 +496,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   const double inv = 1.0 / rnorm;
   for (int i = 0; i < nt; ++i) {
     cd wi{0.0, 0.0};
-    load_tile(t0 + i, false, wi);
+    load_tile(3, i, false, wi);
     wi = correct(i);
     if (q == 0) {
       const int gi = (t0 + i) * PASS_T + r;
