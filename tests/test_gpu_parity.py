@@ -164,6 +164,8 @@ SI_CASES = [
     ("magnetothermal_instabilities", 51, 0.01 + 0.04j, 15, 0),
     ("resistive_tearing", 301, 0.3 - 0.2j, 20, 0),
     ("magnetothermal_instabilities", 501, 0.02 + 0.03j, 20, 0),
+    # BASELINE config 3 at its full size
+    ("resistive_tearing", 5001, 0.3 - 0.2j, 20, 0),
 ]
 
 
@@ -262,3 +264,27 @@ def test_call_order_errors(ctx):
         c2.factorize(1.0 + 0j)
     assert err.value.code == -3
     c2.close()
+
+
+def test_config2_suydam_cluster_behaves_like_the_reference_path(ctx):
+    """BASELINE config 2 at full size (suydam_cluster, G = 1001, nev = 10 next to the cluster).  The
+    Suydam modes accumulate: with the reference's defaults (maxiter = 100 restarts, tol = 5e-15) the
+    reference-equivalent CPU path stops at maxiter with 2 of the 10 pairs converged (861 operator
+    applications).  The device path must do the same - info = 1, the same converged pairs to
+    1e-8 - rather than report more or fewer."""
+    name, gridpts, sigma, nev = "suydam_cluster", 1001, -0.13 + 0.005j, 10
+    s, grid, fields = heq.EQUILIBRIA[name](gridpts)
+    so, go, xgo, fo = oeq.EQUILIBRIA[name](gridpts=gridpts)
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert", number_of_eigenvalues=nev, sigma=sigma)
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    omega, vr, cfg, stats = lb.solve_evp(mats, s)
+    om_o, vr_o, st_o = osolvers.shift_invert(A.to_band(), B.to_band(), 31, 31, sigma, nev, return_stats=True)
+    assert 0 < st_o["nconv"] < nev                       # the premise: the CPU path does not get all ten
+    assert stats["info"] == 1 and stats["nconv"] == st_o["nconv"]
+    got = omega[np.isfinite(omega)]
+    assert got.size == st_o["nconv"]
+    for w in got:
+        j = int(np.argmin(np.abs(om_o - w)))
+        assert abs(om_o[j] - w) <= 1e-8 * abs(w)
+    assert abs(stats["n_op"] - st_o["n_op"]) <= 0.25 * st_o["n_op"]
