@@ -103,6 +103,8 @@ struct lgpu_ctx {
   DevBuf<int32_t> ef_idx;
   DevBuf<cd> bell_val;          // compressed copy of B for the operator application
   DevBuf<int32_t> bell_col, bell_width;
+  DevBuf<double> bell_rval;
+  bool bell_real = false;       // every entry of B is real: the product streams the 8-byte copy
   int bell_w = -1;              // longest row of B; -1: not built for the current B
   bool have_grid = false;       // grid_copy matches the resident matrices
   DevBuf<unsigned long long> d_sync;
@@ -382,18 +384,21 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
   slu_factorize(c->splan, c->sdev(), sigma, c->stream, &c->log);
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
-  int32_t info = 0, bwidth = c->bell_w;
+  int32_t info = 0;
+  int32_t bmeta[2] = {c->bell_w, c->bell_real ? 0 : 1};   // longest row, any imaginary entry
   if (c->bell_w < 0) {   // B changed since the last factorisation: refresh its compressed copy
     const size_t rows = static_cast<size_t>(c->N);
     c->bell_val.ensure(rows * ELL_MAX_WIDTH);
     c->bell_col.ensure(rows * ELL_MAX_WIDTH);
-    c->bell_width.ensure(1);
-    bell_build(c->G, c->B.p, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->stream, &c->log);
-    CUDA_CHECK(cudaMemcpyAsync(&bwidth, c->bell_width.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->bell_width.ensure(2);
+    c->bell_rval.ensure(rows * ELL_MAX_WIDTH);
+    bell_build(c->G, c->B.p, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p, c->bell_rval.p}, c->stream, &c->log);
+    CUDA_CHECK(cudaMemcpyAsync(bmeta, c->bell_width.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_CHECK(cudaMemcpyAsync(&info, c->d_info.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  c->bell_w = bwidth;
+  c->bell_w = bmeta[0];
+  c->bell_real = bmeta[1] == 0;
   float ms = 0.f;
   CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->t_factor = ms;
@@ -431,7 +436,7 @@ void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
   if (c->factor_of_B) return dev_apply_op_general(c, x, y, refine);
   static const bool use_ell = [] { const char* e = std::getenv("LGPU_B_ELL"); return !(e && e[0] == '0'); }();
   if (use_ell && c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
-    bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->bell_w, x, c->vu.p, c->stream,
+    bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p, c->bell_rval.p}, c->bell_w, c->bell_real, x, c->vu.p, c->stream,
                 &c->log);
   else
     block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, c->vu.p, c->stream,
@@ -932,7 +937,7 @@ void fetch_dots(lgpu_ctx* c, cd out[3]) {
 
 void dev_bx(lgpu_ctx* c, const cd* x, cd* y) {
   if (c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
-    bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p}, c->bell_w, x, y, c->stream, &c->log);
+    bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p, c->bell_rval.p}, c->bell_w, c->bell_real, x, y, c->stream, &c->log);
   else
     block_matvec(c->G, c->A.p, c->B.p, cd{0.0, 0.0}, cd{1.0, 0.0}, x, nullptr, y, c->stream, &c->log);
 }

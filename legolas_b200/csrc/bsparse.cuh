@@ -18,13 +18,17 @@ constexpr int ELL_MAX_WIDTH = 16;
 struct BEll {
   cd* val;         // [ELL_MAX_WIDTH][rows]
   int32_t* col;    // [ELL_MAX_WIDTH][rows]
-  int32_t* width;  // device scalar: longest row found by the last build
+  int32_t* width;  // device, 2 ints: [0] longest row found by the last build, [1] != 0 if any entry of
+                   // B has an imaginary part (only with Hall / electron inertia, smod_hall_matrix.f08:6-86)
+  double* rval;    // [ELL_MAX_WIDTH][rows] real parts: the product streams 12 instead of 20 bytes per
+                   // entry when B is real (the reference itself writes B as a real matrix, mod_output.f08:494)
 };
 
 // Compact the (n, 3, 16, 16) block rows of B; *ell.width = max entries per row (may exceed
 // ELL_MAX_WIDTH, in which case the ELL copy is unusable).
 void bell_build(int n, const cd* B, const BEll& ell, cudaStream_t stream, LaunchLog* log);
-// y = B x using `width` entries per row
-void bell_matvec(int n, const BEll& ell, int width, const cd* x, cd* y, cudaStream_t stream, LaunchLog* log);
+// y = B x using `width` entries per row; real_only: every stored entry has a zero imaginary part
+void bell_matvec(int n, const BEll& ell, int width, bool real_only, const cd* x, cd* y, cudaStream_t stream,
+                 LaunchLog* log);
 
 }  // namespace lgpu
