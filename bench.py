@@ -369,7 +369,7 @@ def run_gpu(args):
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
                          "us_per_launch": round(1e3 * ms / cnt, 2), "launches": int(cnt)},
-            "op_roofline": {"what": "whole OP*x = (A - sigma B)^-1 B x (6 kernels), 37120*G algorithmic bytes",
+            "op_roofline": {"what": "whole OP*x = (A - sigma B)^-1 B x (4 launches: B x, forward stage 0, fused upper stages + top system, backward stage 0), 37120*G algorithmic bytes",
                             "achieved": round(op_gbs, 1) if op_gbs else None, "unit": "GB/s",
                             "frac": round(op_gbs / peak, 4) if op_gbs else None,
                             "us_per_op": round(1e3 * op_ms / max(n_op_total, 1), 2)},

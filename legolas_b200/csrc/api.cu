@@ -107,7 +107,6 @@ struct lgpu_ctx {
   bool bell_real = false;       // every entry of B is real: the product streams the 8-byte copy
   int bell_w = -1;              // longest row of B; -1: not built for the current B
   bool have_grid = false;       // grid_copy matches the resident matrices
-  DevBuf<unsigned long long> d_sync;
   DevBuf<cd> mbox;              // mailboxes of the fused solve stages (slu.cuh)
   unsigned long long solve_epoch = 0;
   bool factorized = false;
@@ -135,7 +134,7 @@ struct lgpu_ctx {
     SluDevice d{};
     d.A = factor_of_B ? B.p : A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
     d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
-    d.sync = d_sync.p; d.epoch = &solve_epoch; d.padmask = padmask; d.mbox = mbox.p;
+    d.epoch = &solve_epoch; d.padmask = padmask; d.mbox = mbox.p;
     return d;
   }
 };
@@ -371,13 +370,10 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
     c->gvec.ensure(std::max<size_t>(c->splan.pair_records, 1) * SB);
     c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
     c->d_info.ensure(1);
-    c->d_sync.ensure(SLU_SYNC_COUNTERS);
     c->mbox.ensure(slu_mbox_elems(c->splan));
   }
   ensure_vectors(c);
   c->log.stream = c->stream;
-  // the fused solve stages count finished chunks cumulatively from here on
-  CUDA_CHECK(cudaMemsetAsync(c->d_sync.p, 0, sizeof(unsigned long long) * SLU_SYNC_COUNTERS, c->stream));
   c->solve_epoch = 0;
   // every mailbox entry empty (all-ones NaN) before the first solve with these factors
   CUDA_CHECK(cudaMemsetAsync(c->mbox.p, 0xFF, sizeof(cd) * slu_mbox_elems(c->splan), c->stream));

@@ -588,8 +588,6 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
 struct FusedArgs {
   int nst;                       // fused stages; the last one is the top stage
   int ns, nu, cmax;              // ring shapes, rows of the widest chunk
-  unsigned long long epoch;      // 1, 2, ... since the counters were cleared
-  unsigned long long* sync;      // 2 * MAX_FUSED counters
   StageArgs st[MAX_FUSED];
 };
 
@@ -1258,8 +1256,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     widest.mu = mu_max;
     const RingShape sh = bwd_shape(widest, true);
     f.ns = sh.ns; f.nu = sh.nu;
-    f.sync = d.sync;
-    f.epoch = ++*d.epoch;
+    ++*d.epoch;
     void* args[] = {&f};
     log->begin(LK_TOP, top_bytes);
     CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(slu_fused_stage_kernel), dim3(f.st[0].nchunks),

@@ -99,7 +99,6 @@ struct SluDevice {
   cd* gvec;             // plan.pair_records * 32  (pivot-row right-hand sides of the last solve)
   cd* xpad;             // n_pad * 16 solution scratch when n is odd
   int32_t* info;        // singular-pivot report (1-based block row, 0 = none)
-  unsigned long long* sync;    // SLU_SYNC_COUNTERS device counters (unused by the mailbox hand-off)
   unsigned long long* epoch;   // host: solves since the factorisation; its parity selects the mailbox
   // Mailboxes of the fused upper stages (slu_mbox_elems() complex, every byte 0xFF after a
   // factorisation): two copies (solve parity) of [stage right-hand sides | solved super nodes].
@@ -110,7 +109,6 @@ struct SluDevice {
   uint32_t padmask;     // bit i: row/column i of every 16-wide block belongs to a variable that is not
                         // in the state vector (hd / hd-1d): treated as a decoupled identity row
 };
-constexpr int SLU_SYNC_COUNTERS = 16;
 inline size_t slu_mbox_half(const SluPlan& p) { return (p.rhs_vecs + static_cast<size_t>(p.K)) * SB; }
 inline size_t slu_mbox_elems(const SluPlan& p) { return 2 * slu_mbox_half(p); }
 
