@@ -735,6 +735,8 @@ void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const Kr
   CUDA_CHECK(cudaGetLastError());
 }
 
+// dynamic shared memory the fused step may use: the 227 KB of an SM less its ~1.1 KB of static data
+constexpr size_t CGS2_SMEM_MAX = 225 * 1024;
 static size_t cgs2_smem(int ncols, int nstages, int tiles_max) {
   return sizeof(cd) * (static_cast<size_t>(nstages) * (ncols + 1) * PASS_T + static_cast<size_t>(tiles_max) * PASS_T +
                        2 * PASS_GROUPS * PASS_T + KRYLOV_PASS_MAXCOL) + 16 * nstages;
@@ -744,7 +746,8 @@ template <int CPG>
 static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(CGS2_SMEM_MAX)));
     configured = true;
   }
   void* args[] = {const_cast<CgsArgs*>(&a)};
@@ -763,9 +766,9 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   const bool exact = exact_ok && cpg >= 5 && cpg <= 10 && PASS_GROUPS * cpg <= L.ncv;
   const int ncopy = exact ? PASS_GROUPS * cpg : ncols;
   int nstages = 5;
-  while (nstages > 2 && cgs2_smem(ncopy, nstages, tiles_max) > 210 * 1024) --nstages;
+  while (nstages > 2 && cgs2_smem(ncopy, nstages, tiles_max) > CGS2_SMEM_MAX) --nstages;
   if (!enabled || ncols < 1 || ncols > KRYLOV_PASS_MAXCOL || work.gbar == nullptr || grid > CGS_MAX_GRID ||
-      cgs2_smem(ncopy, nstages, tiles_max) > 210 * 1024)
+      cgs2_smem(ncopy, nstages, tiles_max) > CGS2_SMEM_MAX)
     return false;
   CgsArgs a{};
   a.L = L; a.V = V; a.ncols = ncols; a.nstages = nstages; a.tiles_max = tiles_max; a.w = w;
