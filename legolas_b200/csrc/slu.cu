@@ -740,11 +740,12 @@ constexpr int WLD = 97;   // padded row length of the 64 x 96 working matrix
 __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* W = reinterpret_cast<cd*>(smem_raw);          // [64][WLD]
-  cd* lcol = W + 64 * WLD;                          // [64]
+  cd* lcol = W + 64 * WLD;                          // [64] multipliers of the first column of a double step
+  cd* lcol1 = lcol + 64;                            // [64] ... of the second
   // inverse of L11: lives in rows 32..63, columns 32..63 of W once the reduced rows stored there
   // have been written out (keeps the CTA at 100 KB of shared memory: two CTAs per SM)
   cd* X = W + 32 * WLD + 32;                        // X(i, c) at X[i * WLD + c]
-  int* prm = reinterpret_cast<int*>(lcol + 64);     // [64]
+  int* prm = reinterpret_cast<int*>(lcol1 + 64);    // [64]
   __shared__ double rscale[64];
   const int tid = threadIdx.x;
   const int p = blockIdx.x;
@@ -783,63 +784,101 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     W[i * WLD + c] = W[i * WLD + c] * rscale[i];
   }
   __syncthreads();
-  // 32 elimination steps.  Warp 0 does the sequential part of a step on its own (pivot search,
-  // row swap, multipliers: warp-synchronous, no CTA barrier), then all 8 warps apply the rank-1
-  // update: thread = (column c mod 32, row group), no index arithmetic in the loop.
+  // 32 elimination steps, two at a time.  Warp 0 does the sequential part of both steps on its own
+  // (pivot search, row swap, multipliers of column k; column k+1 and row k+1 brought up to date
+  // under pivot k; pivot search, swap and multipliers of column k+1: warp-synchronous, no CTA
+  // barrier), then all 8 warps apply the two rank-1 updates in ONE pass over the panel: thread =
+  // (column c mod 32, row group).  Same pivots and the same FMA sequence per entry as one step at
+  // a time (bit-identical factors), half the shared-memory traffic and CTA barriers - the
+  // updates are bound by shared-memory wavefronts, not by the FP64 pipe (profiles/fp64_pipe_r1.md).
   const int lane = tid & 31, rg = tid >> 5;
-  for (int k = 0; k < SB; ++k) {
+  // partial pivoting over rows k .. 63 of column k (two candidates per lane), row swap; warp 0 only
+  auto pivot_and_swap = [&](int k, cd* lc_other) {
+    const int i0 = lane, i1 = lane + 32;
+    double b0 = i0 >= k ? abs2(W[i0 * WLD + k]) : -1.0;
+    const double b1 = abs2(W[i1 * WLD + k]);
+    int bi = i0;
+    if (b1 > b0) { b0 = b1; bi = i1; }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, b0, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > b0 || (ob == b0 && oi < bi)) { b0 = ob; bi = oi; }
+    }
+    const int pr = bi;   // the butterfly leaves the same (value, index) in every lane
+    if (lane == 0 && !(b0 > 0.0)) {   // exactly singular panel column: report like zgbtrf info > 0
+      const long long node = (static_cast<long long>(2 * p + 1) << a.level);
+      atomicCAS(a.info, 0, static_cast<int>(min(2 * node + 1, static_cast<long long>(a.n))));
+      W[pr * WLD + k] = cd{2.2250738585072014e-308, 0.0};
+    }
+    __syncwarp();
+    if (pr != k) {
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int c = lane + 32 * cc;
+        const cd t0 = W[k * WLD + c];
+        W[k * WLD + c] = W[pr * WLD + c];
+        W[pr * WLD + c] = t0;
+      }
+      if (lane == 0) {
+        const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0;
+        if (lc_other) { const cd t1 = lc_other[k]; lc_other[k] = lc_other[pr]; lc_other[pr] = t1; }
+      }
+    }
+    __syncwarp();
+  };
+  // multipliers of column k (rows > k), kept in place and in lc
+  auto multipliers = [&](int k, cd* lc) {
+    const cd pinv = crecip(W[k * WLD + k]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = lane + 32 * h;
+      if (i > k) {
+        const cd l = W[i * WLD + k] * pinv;
+        lc[i] = l;
+        W[i * WLD + k] = l;
+      }
+    }
+    __syncwarp();
+  };
+  for (int k = 0; k < SB; k += 2) {
     if (tid < 32) {
-      // partial pivoting over rows k .. 63 of column k (two candidates per lane)
-      const int i0 = tid, i1 = tid + 32;
-      double b0 = i0 >= k ? abs2(W[i0 * WLD + k]) : -1.0;
-      const double b1 = abs2(W[i1 * WLD + k]);
-      int bi = i0;
-      if (b1 > b0) { b0 = b1; bi = i1; }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, b0, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-        if (ob > b0 || (ob == b0 && oi < bi)) { b0 = ob; bi = oi; }
-      }
-      const int pr = bi;   // the butterfly leaves the same (value, index) in every lane
-      if (tid == 0 && !(b0 > 0.0)) {   // exactly singular panel column: report like zgbtrf info > 0
-        const long long node = (static_cast<long long>(2 * p + 1) << a.level);
-        atomicCAS(a.info, 0, static_cast<int>(min(2 * node + 1, static_cast<long long>(a.n))));
-        W[pr * WLD + k] = cd{2.2250738585072014e-308, 0.0};
-      }
-      __syncwarp();
-      if (pr != k) {
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-          const int c = lane + 32 * cc;
-          const cd t0 = W[k * WLD + c];
-          W[k * WLD + c] = W[pr * WLD + c];
-          W[pr * WLD + c] = t0;
-        }
-        if (lane == 0) { const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0; }
-      }
-      __syncwarp();
-      const cd pinv = crecip(W[k * WLD + k]);
+      pivot_and_swap(k, nullptr);
+      multipliers(k, lcol);
+      // column k + 1 under pivot k
+      const cd wk1 = W[k * WLD + k + 1];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int i = lane + 32 * h;
-        if (i > k) {
-          const cd l = W[i * WLD + k] * pinv;
-          lcol[i] = l;
-          W[i * WLD + k] = l;   // multiplier kept in place
-        }
+        if (i > k) cfms(W[i * WLD + k + 1], lcol[i], wk1);
       }
+      __syncwarp();
+      pivot_and_swap(k + 1, lcol);   // the multipliers of column k move with their rows
+      // row k + 1 under pivot k
+      const cd lk1 = lcol[k + 1];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const int c = lane + 32 * cc;
+        if (c > k + 1) cfms(W[(k + 1) * WLD + c], lk1, W[k * WLD + c]);
+      }
+      __syncwarp();
+      multipliers(k + 1, lcol1);
     }
     __syncthreads();
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
       const int c = lane + 32 * cc;
-      if (c > k) {
-        const cd wk = W[k * WLD + c];
+      if (c > k + 1) {
+        const cd wk = W[k * WLD + c], wk1 = W[(k + 1) * WLD + c];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int i = rg + 8 * r;
-          if (i > k) cfms(W[i * WLD + c], lcol[i], wk);
+          if (i > k + 1) {
+            cd x = W[i * WLD + c];
+            cfms(x, lcol[i], wk);
+            cfms(x, lcol1[i], wk1);
+            W[i * WLD + c] = x;
+          }
         }
       }
     }
@@ -1122,7 +1161,7 @@ RingShape bwd_shape(const StageArgs& a, bool top) {
   return RingShape{ns, nu, bytes(ns, nu)};
 }
 
-constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + 64) + sizeof(int) * 64;   // 100.6 KB: two CTAs per SM
+constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + 128) + sizeof(int) * 64;   // 100.6 KB: two CTAs per SM
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
