@@ -734,18 +734,18 @@ __global__ void __launch_bounds__(256) slu_build_rows_kernel(FactorArgs a) {
 }
 
 constexpr int WLD = 97;   // padded row length of the 64 x 96 working matrix
+constexpr int NBF = 4;    // elimination steps per pass over the panel (divides 32)
 
 // Merge rows (2p, 2p+1) of a level: GE with partial pivoting over the 64 stacked rows of the
 // panel [T_2p ; S_2p+1]; block npairs (if present) carries the odd last row up unchanged.
 __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* W = reinterpret_cast<cd*>(smem_raw);          // [64][WLD]
-  cd* lcol = W + 64 * WLD;                          // [64] multipliers of the first column of a double step
-  cd* lcol1 = lcol + 64;                            // [64] ... of the second
+  cd* lcol = W + 64 * WLD;                          // [NBF][64] multipliers of the columns of a block of steps
   // inverse of L11: lives in rows 32..63, columns 32..63 of W once the reduced rows stored there
   // have been written out (keeps the CTA at 100 KB of shared memory: two CTAs per SM)
   cd* X = W + 32 * WLD + 32;                        // X(i, c) at X[i * WLD + c]
-  int* prm = reinterpret_cast<int*>(lcol1 + 64);    // [64]
+  int* prm = reinterpret_cast<int*>(lcol + NBF * 64);   // [64]
   __shared__ double rscale[64];
   const int tid = threadIdx.x;
   const int p = blockIdx.x;
@@ -784,16 +784,18 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     W[i * WLD + c] = W[i * WLD + c] * rscale[i];
   }
   __syncthreads();
-  // 32 elimination steps, two at a time.  Warp 0 does the sequential part of both steps on its own
-  // (pivot search, row swap, multipliers of column k; column k+1 and row k+1 brought up to date
-  // under pivot k; pivot search, swap and multipliers of column k+1: warp-synchronous, no CTA
-  // barrier), then all 8 warps apply the two rank-1 updates in ONE pass over the panel: thread =
-  // (column c mod 32, row group).  Same pivots and the same FMA sequence per entry as one step at
-  // a time (bit-identical factors), half the shared-memory traffic and CTA barriers - the
-  // updates are bound by shared-memory wavefronts, not by the FP64 pipe (profiles/fp64_pipe_r1.md).
+  // 32 elimination steps, NBF at a time (blocked right-looking LU with look-ahead).  Warp 0 does the
+  // sequential part of a block on its own - for each of its columns: bring the column up to date
+  // under the earlier pivots of the block, pivot search, row swap, bring the new pivot row up to
+  // date, multipliers (warp-synchronous, no CTA barrier) - then all 8 warps apply the NBF rank-1
+  // updates in ONE pass over the panel: thread = (column c mod 32, row group).  Same pivots and
+  // the same FMA sequence per entry as one step at a time (bit-identical factors), 1 / NBF of the
+  // shared-memory traffic and CTA barriers: the updates are bound by shared-memory wavefronts,
+  // not by the FP64 pipe (profiles/fp64_pipe_r1.md).  Measured: NBF = 1 / 2 / 4 / 8 -> 2.90 /
+  // 2.49 / 2.39 / 2.47 ms per factorisation at G = 10 001 (beyond 4 the serial part dominates).
   const int lane = tid & 31, rg = tid >> 5;
   // partial pivoting over rows k .. 63 of column k (two candidates per lane), row swap; warp 0 only
-  auto pivot_and_swap = [&](int k, cd* lc_other) {
+  auto pivot_and_swap = [&](int k, int nprev) {
     const int i0 = lane, i1 = lane + 32;
     double b0 = i0 >= k ? abs2(W[i0 * WLD + k]) : -1.0;
     const double b1 = abs2(W[i1 * WLD + k]);
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
       }
       if (lane == 0) {
         const int t0 = prm[k]; prm[k] = prm[pr]; prm[pr] = t0;
-        if (lc_other) { const cd t1 = lc_other[k]; lc_other[k] = lc_other[pr]; lc_other[pr] = t1; }
+        for (int u = 0; u < nprev; ++u) { const cd t1 = lcol[u * 64 + k]; lcol[u * 64 + k] = lcol[u * 64 + pr]; lcol[u * 64 + pr] = t1; }
       }
     }
     __syncwarp();
@@ -841,42 +843,59 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     }
     __syncwarp();
   };
-  for (int k = 0; k < SB; k += 2) {
+  for (int k = 0; k < SB; k += NBF) {
     if (tid < 32) {
-      pivot_and_swap(k, nullptr);
-      multipliers(k, lcol);
-      // column k + 1 under pivot k
-      const cd wk1 = W[k * WLD + k + 1];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = lane + 32 * h;
-        if (i > k) cfms(W[i * WLD + k + 1], lcol[i], wk1);
-      }
-      __syncwarp();
-      pivot_and_swap(k + 1, lcol);   // the multipliers of column k move with their rows
-      // row k + 1 under pivot k
-      const cd lk1 = lcol[k + 1];
+      for (int j = 0; j < NBF; ++j) {
+        const int kj = k + j;
+        // column k + j under the pivots k .. k + j - 1 of this block
+        if (j > 0) {
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        const int c = lane + 32 * cc;
-        if (c > k + 1) cfms(W[(k + 1) * WLD + c], lk1, W[k * WLD + c]);
+          for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i >= kj) {
+              cd x = W[i * WLD + kj];
+#pragma unroll
+              for (int u = 0; u < j; ++u) cfms(x, lcol[u * 64 + i], W[(k + u) * WLD + kj]);
+              W[i * WLD + kj] = x;
+            }
+          }
+          __syncwarp();
+        }
+        pivot_and_swap(kj, j);   // the multipliers of the earlier columns of the block move with their rows
+        // row k + j under the same pivots
+        if (j > 0) {
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) {
+            const int c = lane + 32 * cc;
+            if (c > kj) {
+              cd x = W[kj * WLD + c];
+#pragma unroll
+              for (int u = 0; u < j; ++u) cfms(x, lcol[u * 64 + kj], W[(k + u) * WLD + c]);
+              W[kj * WLD + c] = x;
+            }
+          }
+          __syncwarp();
+        }
+        multipliers(kj, lcol + j * 64);
       }
-      __syncwarp();
-      multipliers(k + 1, lcol1);
     }
     __syncthreads();
+    const int kl = k + NBF - 1;
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
       const int c = lane + 32 * cc;
-      if (c > k + 1) {
-        const cd wk = W[k * WLD + c], wk1 = W[(k + 1) * WLD + c];
+      if (c > kl) {
+        cd wk[NBF];
+#pragma unroll
+        for (int u = 0; u < NBF; ++u) wk[u] = W[(k + u) * WLD + c];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int i = rg + 8 * r;
-          if (i > k + 1) {
+          if (i > kl) {
             cd x = W[i * WLD + c];
-            cfms(x, lcol[i], wk);
-            cfms(x, lcol1[i], wk1);
+#pragma unroll
+            for (int u = 0; u < NBF; ++u) cfms(x, lcol[u * 64 + i], wk[u]);
             W[i * WLD + c] = x;
           }
         }
@@ -1161,7 +1180,7 @@ RingShape bwd_shape(const StageArgs& a, bool top) {
   return RingShape{ns, nu, bytes(ns, nu)};
 }
 
-constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + 128) + sizeof(int) * 64;   // 100.6 KB: two CTAs per SM
+constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + NBF * 64) + sizeof(int) * 64;   // 100.6 KB: two CTAs per SM
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
