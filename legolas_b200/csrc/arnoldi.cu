@@ -282,12 +282,18 @@ __device__ __forceinline__ void cgs_sum_partials(const cd* partial, int ncols, c
 // How many times slot i % S has been filled before local tile i is streamed in pass `pass` of the
 // fused step (passes run up, down, up over the nt tiles of a CTA; the S tiles a pass ends with stay
 // in their slots for the next pass).  Its parity is the phase of the slot's "full" barrier.
-__device__ __forceinline__ int cgs_fill_number(int pass, int i, int nt, int S) {
-  const int sg = i % S;
-  const int n = (nt - sg + S - 1) / S;        // tiles of this CTA that map to the slot
-  if (pass == 1) return i / S;
-  if (pass == 2) return n + (sg + (n - 1) * S - S - i) / S;   // below the slot's resident tile, downwards
-  return 2 * n - 1 + i / S - 1;               // pass 3: above the slot's resident tile, upwards
+// x / S for 0 <= x < 8192 and 2 <= S <= 8 without an integer division: M = 65536 / S + 1
+struct SmallDiv {
+  int S, M;
+  __host__ __device__ int div(int x) const { return static_cast<int>((static_cast<unsigned>(x) * static_cast<unsigned>(M)) >> 16); }
+  __host__ __device__ int mod(int x) const { return x - div(x) * S; }
+};
+__device__ __forceinline__ int cgs_fill_number(int pass, int i, int nt, const SmallDiv& d) {
+  const int S = d.S, q = d.div(i), sg = i - q * S;
+  const int n = d.div(nt - sg + S - 1);       // tiles of this CTA that map to the slot
+  if (pass == 1) return q;
+  if (pass == 2) return n + d.div(sg + (n - 1) * S - S - i);   // below the slot's resident tile, downwards
+  return 2 * n - 1 + q - 1;                   // pass 3: above the slot's resident tile, upwards
 }
 
 template <int CPG>
@@ -325,9 +331,10 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     // release F - 1 of that slot; only the first pass needs w from global memory.
     if (lane == 0) {
       const int S = nstages;
+      const SmallDiv sd{S, 65536 / S + 1};
       const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncopy * PASS_T);
       auto fill = [&](int i, int F, bool with_w) {
-        const int sg = i % S, t = t0 + i;
+        const int sg = sd.mod(i), t = t0 + i;
         if (F >= 1) mbar_wait(&empty[sg], static_cast<uint32_t>((F - 1) & 1));
         cd* sb = buf + static_cast<size_t>(sg) * sstride;
         const uint32_t wbytes = with_w ? static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T)) : 0u;
@@ -335,9 +342,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         bulk_g2s(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[sg]);
         if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[sg]);
       };
-      for (int i = 0; i < nt; ++i) fill(i, cgs_fill_number(1, i, nt, S), true);
-      for (int i = nt - S - 1; i >= 0; --i) fill(i, cgs_fill_number(2, i, nt, S), false);
-      for (int i = S; i < nt; ++i) fill(i, cgs_fill_number(3, i, nt, S), false);
+      for (int i = 0; i < nt; ++i) fill(i, cgs_fill_number(1, i, nt, sd), true);
+      for (int i = nt - S - 1; i >= 0; --i) fill(i, cgs_fill_number(2, i, nt, sd), false);
+      for (int i = S; i < nt; ++i) fill(i, cgs_fill_number(3, i, nt, sd), false);
     }
     return;
   }
@@ -353,12 +360,13 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   cd v[NJ];
   cd* xw = part;   // [8 warps][PASS_CPG] scratch of the row reduction
 
+  const SmallDiv csd{nstages, 65536 / nstages + 1};
   // local tile i of pass `pass` -> registers (see the producer for the slot / residency rules)
   auto load_tile = [&](int pass, int i, bool want_w, cd& wi) {
-    const int S = nstages, sg = i % S;
+    const int S = nstages, sg = csd.mod(i);
     const bool valid = (t0 + i) * PASS_T + r < L.n;
     const bool resident = (pass == 2 && i >= nt - S) || (pass == 3 && i < S);
-    if (!resident) mbar_wait(&full[sg], static_cast<uint32_t>(cgs_fill_number(pass, i, nt, S) & 1));
+    if (!resident) mbar_wait(&full[sg], static_cast<uint32_t>(cgs_fill_number(pass, i, nt, csd) & 1));
     const cd* sb = buf + static_cast<size_t>(sg) * sstride;
     if (want_w) wi = valid ? sb[ncopy * PASS_T + r] : cd{0.0, 0.0};
     if (EXACT) {   // rows past the end of the basis are zero in memory

@@ -32,11 +32,14 @@ for r in csv.reader(open(csv_path)):
 ci = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 
-# ---- listing: instruction -> (file, line)
-insts, cur, on = [], ("?", 0), False
+# ---- listing: instruction -> (file, line); a template has one section per instantiation: take the
+# one with as many instructions as the captured launch
+sections, cur, on = [], ("?", 0), False
 for ln in open(lst_path):
     if ln.startswith(".text."):
         on = kname in ln
+        if on:
+            sections.append([])
         continue
     if not on:
         continue
@@ -45,7 +48,8 @@ for ln in open(lst_path):
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
-        insts.append(cur)
+        sections[-1].append(cur)
+insts = min(sections, key=lambda sec: abs(len(sec) - len(rows))) if sections else []
 if len(insts) != len(rows):
     print(f"warning: {len(rows)} ncu rows vs {len(insts)} listed instructions", file=sys.stderr)
 
