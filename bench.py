@@ -27,7 +27,14 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The reference arm times the CPU algorithm "with all the host threads it can use": torchrun
+# exports OMP_NUM_THREADS=1 to its workers, which would pin OpenBLAS to one thread.  Must happen
+# before numpy / scipy load their BLAS.
+if "--impl" in sys.argv and "reference" in sys.argv:
+    for _var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_var] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -154,6 +161,12 @@ def run_reference(args):
             vals.append(res["value"])
     value = float(np.mean(vals))
     cores = os.cpu_count() or 1
+    try:   # the threads the BLAS behind scipy actually runs with
+        from threadpoolctl import threadpool_info
+        blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        cores = max(blas) if blas else cores
+    except Exception:
+        pass
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3,
