@@ -519,9 +519,8 @@ class CudaKrylovOps final : public KrylovOps {
     const int nc = kev + 1 <= kplusp ? kev + 1 : kplusp;
     (void)n;
     basis_gemm(c_->basis, c_->V.p, kplusp, c_->Qdev.p, ncv_, nc, c_->V.p, 0, c_->stream, &c_->log);
-    vec_axpby_basis(c_->basis, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
-                    c_->V.p, kev, c_->stream, &c_->log);
-    krylov_update(c_->basis, c_->V.p, 0, c_->resid.p, kwork(c_), c_->stream, &c_->log);
+    vec_axpby_basis_norm(c_->basis, cd{sigmak.real(), sigmak.imag()}, c_->resid.p, cd{betak, 0.0},
+                         c_->V.p, kev, kwork(c_), c_->stream, &c_->log);
   }
 
   void ritz_vectors(int kplusp, int nconv, const cplx* S, int lds) override {

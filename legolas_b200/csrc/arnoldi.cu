@@ -617,6 +617,39 @@ vec_axpby_basis_kernel(BasisLayout L, cd a, cd* __restrict__ r, cd b, const cd* 
   if (i < L.n) r[i] = a * r[i] + b * V[basis_off(L, i, col)];
 }
 
+// r = a*r + b*V(:, col) and scal[0] = ||r|| in one launch (the residual of an implicit restart):
+// CTA partials of the squared norm, the last CTA to finish sums them in a fixed order
+__global__ void __launch_bounds__(256)
+vec_axpby_basis_norm_kernel(BasisLayout L, cd a, cd* __restrict__ r, cd b, const cd* __restrict__ V, int col,
+                            cd* __restrict__ partial, double* scal, unsigned int* ticket) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double nn = 0.0;
+  for (int i = blockIdx.x * 256 + tid; i < L.n; i += gridDim.x * 256) {
+    const cd v = a * r[i] + b * V[basis_off(L, i, col)];
+    r[i] = v;
+    nn += abs2(v);
+  }
+  nn = warp_sum(nn);
+  if (lane == 0) red[warp] = nn;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[static_cast<size_t>(blockIdx.x) * PSTRIDE] = cd{t, 0.0};
+  }
+  if (last_block_done(ticket, tid == 0)) {
+    if (warp == 0) {
+      double t = 0.0;
+      for (unsigned int bb = lane; bb < gridDim.x; bb += 32) t += partial[static_cast<size_t>(bb) * PSTRIDE].x;
+      t = warp_sum(t);
+      if (lane == 0) scal[0] = sqrt(t);
+    }
+    __syncthreads();
+    if (tid == 0) *ticket = 0u;
+  }
+}
+
 // out[0] = x^H s, out[1] = x^H r (zdotc), out[2] = (||x||^2, 0): CTA partials, the last CTA sums
 // them in a fixed order
 __global__ void __launch_bounds__(256)
@@ -834,6 +867,16 @@ void vec_axpby_basis(const BasisLayout& L, cd a, cd* r, cd b, const cd* V, int c
                      cudaStream_t stream, LaunchLog* log) {
   log->begin(LK_OTHER, 48.0 * L.n);
   vec_axpby_basis_kernel<<<(L.n + 255) / 256, 256, 0, stream>>>(L, a, r, b, V, col);
+  log->end();
+  log->launches += 1;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void vec_axpby_basis_norm(const BasisLayout& L, cd a, cd* r, cd b, const cd* V, int col, const KrylovWork& work,
+                          cudaStream_t stream, LaunchLog* log) {
+  log->begin(LK_OTHER, 48.0 * L.n);
+  const int grid = std::max(1, std::min(2 * sm_count(), (L.n + 255) / 256));
+  vec_axpby_basis_norm_kernel<<<grid, 256, 0, stream>>>(L, a, r, b, V, col, work.partial, work.scal, work.ticket);
   log->end();
   log->launches += 1;
   CUDA_CHECK(cudaGetLastError());

@@ -75,6 +75,9 @@ void basis_gemm(const BasisLayout& L, const cd* V, int nk, const cd* Q, int ldq,
 // r = a*r + b*V(:, col)
 void vec_axpby_basis(const BasisLayout& L, cd a, cd* r, cd b, const cd* V, int col,
                      cudaStream_t stream, LaunchLog* log);
+// r = a*r + b*V(:, col), then scal[0] = ||r||_2 (deterministic), one launch
+void vec_axpby_basis_norm(const BasisLayout& L, cd a, cd* r, cd b, const cd* V, int col, const KrylovWork& work,
+                          cudaStream_t stream, LaunchLog* log);
 // work.hwork[0] = x^H s, [1] = x^H r, [2] = (||x||^2, 0)   (plain vectors; deterministic)
 void vec_dot2(int n, const cd* x, const cd* sv, const cd* rv, const KrylovWork& work, cudaStream_t stream,
               LaunchLog* log);
