@@ -1180,7 +1180,7 @@ RingShape bwd_shape(const StageArgs& a, bool top) {
   return RingShape{ns, nu, bytes(ns, nu)};
 }
 
-constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + NBF * 64) + sizeof(int) * 64;   // 100.6 KB: two CTAs per SM
+constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + NBF * 64) + sizeof(int) * 64;   // 101 KiB: two CTAs per SM
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
