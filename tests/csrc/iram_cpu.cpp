@@ -137,4 +137,33 @@ int dense_schur_reorder(int n, double* T_ri, double* Z_ri, const char* select) {
                                     reinterpret_cast<cplx*>(Z_ri), n, n, sel);
 }
 
+// dense_host.hpp pieces on their own (column-major, interleaved complex): the AVX2 + FMA plane
+// rotations against the scalar ones, and the plane-rotation generator
+int dense_have_avx2() {
+#ifdef LGPU_DENSE_AVX2
+  return lgpu::dense::have_avx2() ? 1 : 0;
+#else
+  return 0;
+#endif
+}
+
+void dense_rot_rows(double* p_ri, int ld, int count, double c, double s_re, double s_im, int simd) {
+  cplx* p = reinterpret_cast<cplx*>(p_ri);
+  if (simd) lgpu::dense::rot_rows(p, ld, count, c, cplx(s_re, s_im));
+  else lgpu::dense::rot_rows_scalar(p, ld, count, c, cplx(s_re, s_im));
+}
+
+void dense_rot_cols(double* a_ri, double* b_ri, int m, double c, double s_re, double s_im, int simd) {
+  cplx* a = reinterpret_cast<cplx*>(a_ri);
+  cplx* b = reinterpret_cast<cplx*>(b_ri);
+  if (simd) lgpu::dense::rot_cols(a, b, m, c, cplx(s_re, s_im));
+  else lgpu::dense::rot_cols_scalar(a, b, m, c, cplx(s_re, s_im));
+}
+
+void dense_lartg(double f_re, double f_im, double g_re, double g_im, double* out5) {
+  double c; cplx s, r;
+  lgpu::dense::lartg(cplx(f_re, f_im), cplx(g_re, g_im), &c, &s, &r);
+  out5[0] = c; out5[1] = s.real(); out5[2] = s.imag(); out5[3] = r.real(); out5[4] = r.imag();
+}
+
 }  // extern "C"

@@ -149,3 +149,49 @@ def test_iram_reports_nonconvergence_like_arpack(lib):
     assert abs(st["nconv"] - st_o["nconv"]) <= 1
     omega = sigma + 1.0 / nu
     assert max(np.min(np.abs(om_o - w)) / abs(w) for w in omega) < 1e-8
+
+
+# ---- dense_host.hpp on its own: SIMD rotations and plane-rotation generation
+def _dptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("count", [0, 1, 2, 7, 40])
+def test_simd_rotations_match_scalar_and_numpy(lib, count):
+    lib.dense_rot_rows.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+    lib.dense_rot_cols.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+    rng = np.random.default_rng(3 + count)
+    ld = 43
+    c, s = 0.8, 0.6 * np.exp(0.7j)
+    # rows (i, i+1) of a column-major matrix over `count` columns
+    M = np.asfortranarray(rng.standard_normal((ld, 45)) + 1j * rng.standard_normal((ld, 45)))
+    ref = M.copy(order="F")
+    x, y = ref[5, 3:3 + count].copy(), ref[6, 3:3 + count].copy()
+    ref[5, 3:3 + count], ref[6, 3:3 + count] = c * x + s * y, -np.conj(s) * x + c * y
+    for simd in (0, 1):
+        W = M.copy(order="F")
+        lib.dense_rot_rows(C.c_void_p(W.ctypes.data + 16 * (3 * ld + 5)), ld, count, c, s.real, s.imag, simd)
+        assert np.abs(W - ref).max() <= 4e-16 * max(np.abs(ref).max(), 1.0), simd
+    # two columns over `count` rows
+    a0 = rng.standard_normal(count) + 1j * rng.standard_normal(count)
+    b0 = rng.standard_normal(count) + 1j * rng.standard_normal(count)
+    for simd in (0, 1):
+        a, b = a0.copy(), b0.copy()
+        lib.dense_rot_cols(_dptr(a), _dptr(b), count, c, s.real, s.imag, simd)
+        assert np.abs(a - (c * a0 + np.conj(s) * b0)).max(initial=0.0) <= 4e-16 * 3
+        assert np.abs(b - (-s * a0 + c * b0)).max(initial=0.0) <= 4e-16 * 3
+
+
+@pytest.mark.parametrize("f,g", [(1.0 + 2.0j, -0.5 + 0.25j), (3e-200j, 1e-190), (0.0j, 2.0 - 1.0j), (1.5 + 0j, 0.0j),
+                                 (1e160 + 1e160j, 2e159 - 1e150j)])
+def test_plane_rotation_annihilates_second_entry(lib, f, g):
+    """zlartg contract on both branches (unscaled fast path and the scaled one): real c, c^2 + |s|^2 = 1,
+    [c s; -conj(s) c] [f; g] = [r; 0]."""
+    lib.dense_lartg.argtypes = [C.c_double] * 4 + [C.c_void_p]
+    out = np.zeros(5)
+    lib.dense_lartg(f.real, f.imag, complex(g).real, complex(g).imag, _dptr(out))
+    c, s, r = out[0], out[1] + 1j * out[2], out[3] + 1j * out[4]
+    scale = max(abs(f), abs(g))
+    assert abs(c * c + abs(s) ** 2 - 1.0) <= 1e-14
+    assert abs(c * f + s * g - r) <= 1e-14 * scale
+    assert abs(-np.conj(s) * f + c * g) <= 1e-14 * scale
