@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     if (lane == 0) {
       const int S = nstages;
       const SmallDiv sd{S, 65536 / S + 1};
+      const uint64_t keep_policy = l2_policy_evict_last();
       const uint32_t vbytes = static_cast<uint32_t>(sizeof(cd) * ncopy * PASS_T);
       auto fill = [&](int i, int F, bool with_w) {
         const int sg = sd.mod(i), t = t0 + i;
@@ -339,7 +340,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         cd* sb = buf + static_cast<size_t>(sg) * sstride;
         const uint32_t wbytes = with_w ? static_cast<uint32_t>(sizeof(cd) * min(PASS_T, L.n - t * PASS_T)) : 0u;
         mbar_expect_tx(&full[sg], vbytes + wbytes);
-        bulk_g2s(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[sg]);
+        // the basis (<= ~100 MB) is re-read by every step and fits the 126 MB L2 next to the upper-level
+        // factor records; the stage-0 records of the solve in between stream through with evict-first
+        bulk_g2s_hint(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[sg], keep_policy);
         if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[sg]);
       };
       for (int i = 0; i < nt; ++i) fill(i, cgs_fill_number(1, i, nt, sd), true);
