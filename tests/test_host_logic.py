@@ -94,3 +94,60 @@ def test_host_sampling_matches_oracle(name, kw):
     assert set(fields) == set(fo)
     for key, ref in fo.items():
         assert np.abs(fields[key] - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), key
+
+
+def test_cgs2_ring_protocol_model():
+    """Model of the shared-memory ring of the fused Gram-Schmidt step (legolas_b200/csrc/arnoldi.cu,
+    cgs_fill_number / load_tile / the producer lane): local tile i lives in slot i % S, the three
+    passes visit the CTA's tiles up / down / up, the S tiles a pass ends with stay resident for the
+    next one.  Checked here for every shape: per slot the producer's fill numbers are 0, 1, 2, ... in
+    issue order (they select the mbarrier phase), a fill is only issued after the release that
+    precedes it, every visit finds its own tile in its slot, and nothing deadlocks.  The device code
+    evaluates the same formulas with a multiply-shift division, checked as well."""
+    def fill_number(p, i, nt, S):
+        sg = i % S
+        n = (nt - sg + S - 1) // S
+        if p == 1:
+            return i // S
+        if p == 2:
+            return n + (sg + (n - 1) * S - S - i) // S
+        return 2 * n - 1 + i // S - 1
+
+    for S in range(2, 9):
+        M = 65536 // S + 1
+        assert all((x * M) >> 16 == x // S for x in range(8192))
+        for nt in range(1, 48):
+            fills = ([(1, i) for i in range(nt)] + [(2, i) for i in range(nt - S - 1, -1, -1)]
+                     + [(3, i) for i in range(S, nt)])
+            issued, number = {}, {}
+            for p, i in fills:
+                F = fill_number(p, i, nt, S)
+                assert issued.get(i % S, 0) == F, (S, nt, p, i)
+                issued[i % S] = F + 1
+                number[(p, i)] = F
+            pending, content, releases = list(fills), {}, {}
+
+            def produce():
+                while pending:
+                    p, i = pending[0]
+                    F = number[(p, i)]
+                    if F >= 1 and releases.get(i % S, 0) < F:
+                        return
+                    content[i % S] = (i, F)
+                    pending.pop(0)
+
+            produce()
+            visits = ([(1, i) for i in range(nt)] + [(2, i) for i in range(nt - 1, -1, -1)]
+                      + [(3, i) for i in range(nt)])
+            for p, i in visits:
+                sg = i % S
+                resident = (p == 2 and i >= nt - S) or (p == 3 and i < S)
+                if not resident:
+                    produce()
+                    assert content.get(sg, (None, -1))[1] == fill_number(p, i, nt, S), (S, nt, p, i)
+                assert content[sg][0] == i, (S, nt, p, i)
+                keep = (p == 1 and i >= nt - S) or (p == 2 and i < S)
+                if not keep:
+                    releases[sg] = releases.get(sg, 0) + 1
+                    produce()
+            assert not pending
