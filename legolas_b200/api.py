@@ -40,6 +40,7 @@ STATE_VECTORS = {"mhd": ("rho", "v1", "v2", "v3", "T", "a1", "a2", "a3"),
 GEOMETRIES = {"Cartesian": 0, "cylindrical": 1}
 BOUNDARY_TYPES = {"wall": 0, "wall_weak": 1}
 ALLOWED_WHICH = ("LM", "SM", "LR", "SR", "LI", "SI")
+MAX_NCV = 128   # KRYLOV_MAXCOL of csrc/arnoldi.cuh
 
 
 class LegolasError(RuntimeError):
@@ -78,6 +79,7 @@ class Settings:
     heating: bool = False
     conduction: bool = False
     perpendicular_conduction: bool = False
+    parallel_conduction: Optional[bool] = None   # None: on whenever conduction is (datfile header only)
     viscosity: bool = False
     viscosity_value: float = 0.0
     viscous_heating: bool = False
@@ -176,6 +178,9 @@ def new_arpack_config(evpdim: int, mode: int, bmat: str, solver_settings: Solver
         raise LegolasError(f"ncv too low, expected ncv - nev >= 1 but got ncv - nev = {ncv - nev}")
     if ncv > evpdim:
         raise LegolasError(f"ncv too high, expected ncv < N but got ncv = {ncv} and N = {evpdim}")
+    if ncv > MAX_NCV:
+        raise LegolasError(f"ncv = {ncv} exceeds the {MAX_NCV} basis columns the device Arnoldi kernels hold "
+                           f"(number_of_eigenvalues <= {MAX_NCV // 2} with the default ncv = 2 nev)")
     maxiter = solver_settings.maxiter
     if maxiter < 0:
         raise LegolasError(f"Arnoldi: maxiter must be positive, but is equal to {maxiter}")
@@ -338,28 +343,26 @@ class Context:
         self._check(self._lib.lgpu_factorize(self._h, sigma.real, sigma.imag, C.byref(info)), "factorize")
         return info.value
 
-    def _vec_call(self, fn, what, x, *extra):
+    def _vec(self, x, what: str) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.complex128)
         if x.shape != (self.dim,):
-            raise LegolasError(f"{what}: vector length {x.shape} != matrix dimension {self.dim}")
-        y = np.empty_like(x)
-        self._check(fn(self._h, *extra[:1], x.ctypes.data, y.ctypes.data, *extra[1:]), what)
-        return y
+            raise LegolasError(f"{what}: vector of shape {x.shape}, matrix dimension is {self.dim}")
+        return x
 
     def solve(self, rhs, refine_steps: int = 0) -> np.ndarray:
-        rhs = np.ascontiguousarray(rhs, dtype=np.complex128)
+        rhs = self._vec(rhs, "solve")
         x = np.empty_like(rhs)
         self._check(self._lib.lgpu_solve(self._h, rhs.ctypes.data, x.ctypes.data, refine_steps), "solve")
         return x
 
     def matvec(self, which: str, x) -> np.ndarray:
-        x = np.ascontiguousarray(x, dtype=np.complex128)
+        x = self._vec(x, "matvec")
         y = np.empty_like(x)
         self._check(self._lib.lgpu_matvec(self._h, _which(which), x.ctypes.data, y.ctypes.data), "matvec")
         return y
 
     def apply_op(self, x, refine_steps: int = 0) -> np.ndarray:
-        x = np.ascontiguousarray(x, dtype=np.complex128)
+        x = self._vec(x, "apply_op")
         y = np.empty_like(x)
         self._check(self._lib.lgpu_apply_op(self._h, x.ctypes.data, y.ctypes.data, refine_steps), "apply_op")
         return y
@@ -376,6 +379,9 @@ class Context:
         read-back buffer (valid until the next solve on this context) instead of a copy."""
         ca = _arnoldi_c(cfg, sigma, refine_steps)
         resid = np.ascontiguousarray(cfg.residual, dtype=np.complex128)
+        if cfg.evpdim != self.dim or resid.shape != (self.dim,):
+            raise LegolasError(f"Arnoldi: evpdim = {cfg.evpdim} / start vector of shape {resid.shape} do not match "
+                               f"the resident matrices (dimension {self.dim})")
         omega = np.empty(cfg.nev, dtype=np.complex128)
         vr = None
         if want_vectors:
@@ -469,12 +475,8 @@ def pinned_empty(shape, dtype=np.complex128, order="F") -> np.ndarray:
     block = _PinnedBlock(lib, max(count * dt.itemsize, 1))
     buf = (C.c_char * block.nbytes).from_address(block.ptr)
     arr = np.frombuffer(buf, dtype=dt, count=count).reshape(shape, order=order)
-    _PINNED_OWNERS[id(buf)] = block          # keep the allocation alive with the buffer object
-    buf._owner = block
+    buf._owner = block          # the ctypes buffer (base of the array) keeps the allocation alive
     return arr
-
-
-_PINNED_OWNERS = {}
 
 
 def _which(which: str) -> int:
@@ -495,6 +497,28 @@ def _arnoldi_c(cfg: ArpackConfig, sigma: complex, refine_steps: int) -> CArnoldi
 
 def _stats_dict(st: CStats) -> dict:
     return {name: getattr(st, name) for name, _ in CStats._fields_ if name != "reserved"}
+
+
+def _parse_arnoldi_status(stats: dict, cfg) -> None:
+    """parse_znaupd_info / parse_zneupd_info (src/solvers/arnoldi/mod_arpack_type.f08:364-436) and
+    the zgbtrf info check (src/solvers/mod_linear_systems.f08:125-137): info = 1 (maxiter reached)
+    and a singular pivot are warnings, every other non-zero info is logger%error, i.e. raises."""
+    import warnings
+
+    if stats.get("lu_info", 0) != 0:
+        warnings.warn(f"LAPACK routine zgbtrf failed! info = {stats['lu_info']}", RuntimeWarning, stacklevel=3)
+    info = stats["info"]
+    if info == 0:
+        return
+    if info == 1:
+        warnings.warn(f"ARPACK failed to converge! (maxiter reached) number of iterations: {cfg.maxiter}, "
+                      f"number of converged eigenvalues: {stats['nconv']} / {cfg.nev}", RuntimeWarning, stacklevel=3)
+        return
+    messages = {3: "znaupd: no shifts could be applied during a cycle of the Arnoldi iteration. Try increasing "
+                   "the size of ncv relative to number_of_eigenvalues.",
+                -8: "znaupd: error LAPACK eigenvalue calculation",
+                -9: "znaupd: starting vector is zero, try rerunning?"}
+    raise LegolasError(messages.get(info, f"znaupd: unexpected info = {info} encountered"))
 
 
 # ------------------------------------------------------------------ reference-named entry points
@@ -543,6 +567,7 @@ def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
         omega, vr, stats = matrices.ctx.arnoldi_general(cfg, sv.refine_steps)
         cfg.info = stats["info"]
         cfg.iparam.update({5: stats["nconv"], 9: stats["n_op"], 10: stats["n_bx"], 11: stats["n_reorth"]})
+        _parse_arnoldi_status(stats, cfg)
         return omega, vr, cfg, stats
     if sv.arpack_mode != "shift-invert":
         # smod_arpack_main.f08:78-82
@@ -553,4 +578,5 @@ def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
     omega, vr, stats = matrices.ctx.shift_invert(cfg, complex(sv.sigma), sv.refine_steps, vr_view=vr_view)
     cfg.info = stats["info"]
     cfg.iparam.update({5: stats["nconv"], 9: stats["n_op"], 10: stats["n_bx"], 11: stats["n_reorth"]})
+    _parse_arnoldi_status(stats, cfg)
     return omega, vr, cfg, stats

@@ -362,7 +362,7 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
   if (of_B) sigma = cd{0.0, 0.0};
   if (c->splan.n != c->G) {
     c->splan = make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 2),
-                             env_int("LGPU_SLU_TOP", 8));
+                             env_int("LGPU_SLU_TOP", 2));
     c->pairs.ensure(std::max<size_t>(c->splan.pair_records, 1) * PAIR_STRIDE);
     c->topfac.ensure(TOP_STRIDE);
     c->fwork.ensure(c->splan.work_rows * ROW_STRIDE);

@@ -708,16 +708,7 @@ BasisLayout make_basis_layout(int n, int ncv) {
   return L;
 }
 
-static int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }
 static size_t pass_smem(int ncols, int nstages) {
   return sizeof(cd) * (static_cast<size_t>(nstages) * (ncols + 1) * PASS_T + 2 * PASS_GROUPS * PASS_T +
                        KRYLOV_PASS_MAXCOL) + 16 * nstages;
@@ -726,12 +717,11 @@ static size_t pass_smem(int ncols, int nstages) {
 template <bool UPDATE, bool DOTS>
 static void launch_pass(const BasisLayout& L, const cd* V, int c0, int ncols, cd* w, const KrylovWork& work,
                         cd* Hcol, int accumulate, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  once.run([] {
     CUDA_CHECK(cudaFuncSetAttribute(krylov_pass_kernel<UPDATE, DOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     220 * 1024));
-    configured = true;
-  }
+  });
   int nstages = 6;
   while (nstages > 2 && pass_smem(ncols, nstages) > 200 * 1024) --nstages;
   const int grid = std::max(1, std::min(sm_count(), L.ntiles));
@@ -788,12 +778,11 @@ static size_t cgs2_smem(int ncols, int nstages, int tiles_max) {
 
 template <int CPG>
 static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  once.run([] {
     CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(CGS2_SMEM_MAX)));
-    configured = true;
-  }
+  });
   void* args[] = {const_cast<CgsArgs*>(&a)};
   CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(krylov_cgs2_kernel<CPG>), dim3(grid), dim3(PASS_THREADS),
                                          args, smem, stream));
@@ -848,12 +837,10 @@ void krylov_scale(const BasisLayout& L, const cd* w, cd* V, int col, cd* vplain,
 void basis_gemm(const BasisLayout& L, const cd* V, int nk, const cd* Q, int ldq, int nc, cd* Out,
                 int out_plain_ld, cudaStream_t stream, LaunchLog* log) {
   const size_t smem = sizeof(cd) * (static_cast<size_t>(nk) * nc + static_cast<size_t>(nk) * 32);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
-    configured = smem;
-  }
+  static PerDeviceOnce once;
+  once.run([] {
+    CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  });
   log->begin(LK_GEMM, 16.0 * L.n * (nk + nc));
   static const bool rows_path = [] { const char* e = std::getenv("LGPU_GEMM_ROWS"); return !(e && e[0] == '0'); }();
   if (rows_path && nk <= 40 && sizeof(cd) * nk * nc <= 48 * 1024)

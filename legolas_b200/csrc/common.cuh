@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -77,6 +78,36 @@ inline void cuda_check(cudaError_t err, const char* what, const char* file, int 
   }
 }
 #define CUDA_CHECK(expr) ::lgpu::cuda_check((expr), #expr, __FILE__, __LINE__)
+
+// Function attributes (dynamic shared-memory opt-in) and the SM count are per DEVICE: a process may
+// hold contexts on several GPUs (lgpu_create(device = n)), so one-time configuration is keyed by the
+// current device, not by a process-wide flag.
+struct PerDeviceOnce {
+  std::mutex m;
+  uint64_t done = 0;
+  template <typename F>
+  void run(F&& f) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(m);
+    if (dev < 64 && ((done >> dev) & 1ull)) return;
+    f();
+    if (dev < 64) done |= 1ull << dev;
+  }
+};
+inline int device_sm_count() {
+  static std::mutex m;
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(m);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
 
 // Kernel-launch accounting and optional per-kernel-class device timing (CUDA events recorded
 // on the launching stream around each launch; read back at a synchronisation point).

@@ -54,7 +54,8 @@ struct IramConfig {
 };
 
 struct IramResult {
-  int info = 0;       // 0 ok, 1 maxiter reached, 2 no shifts left (np == 0), -9 zero start vector
+  int info = 0;       // znaupd codes: 0 ok, 1 maxiter reached, 3 no shifts could be applied (np == 0),
+                      // -8 error in the small eigen-solve, -9 zero start vector; nconv = 0 on every error
   int nconv = 0;
   int n_op = 0;
   int n_reorth = 0;
@@ -123,7 +124,7 @@ class Iram {
         if (bounds[j] == cplx(0.0)) { --np; ++nev; }
       if (nconv >= nev0 || iter > cfg.maxiter || np == 0) {
         if (iter > cfg.maxiter && nconv < nev0) res.info = 1;
-        if (np == 0 && nconv < nev0) res.info = 2;
+        if (np == 0 && nconv < nev0) res.info = 3;   // znaup2 reports 2, znaupd surfaces it as 3
         break;
       }
       if (nconv < nev0) {
@@ -151,7 +152,7 @@ class Iram {
     res.nconv = std::min(nconv, nev0);
     // Schur form of the final H with all of Q (ritz / bounds of the loop's last pass stay in
     // ritz0 / bounds0)
-    if (res.nconv > 0 && neigh(kplusp, rnorm, T, Q, ritz, bounds, true) != 0) { res.info = -8; return res; }
+    if (res.nconv > 0 && neigh(kplusp, rnorm, T, Q, ritz, bounds, true) != 0) { res.info = -8; res.nconv = 0; return res; }
     extract(ops, cfg, kplusp, nev0, np0, res.nconv, tol, eps23, rnorm, ritz0, bounds0, T, Q, res);
     return res;
   }

@@ -81,6 +81,12 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __device__ __forceinline__ int tri_lo_off(int c) { return c * SB - (c * (c - 1)) / 2; }
 __device__ __forceinline__ int tri_up_off(int k) { return (k * (k + 1)) / 2; }
 
+// Programmatic dependent launch: wait = the kernels before this one on the stream have completed and
+// their writes are visible (no-op for a plain launch); launch_dependents = the next kernel's CTAs may be
+// scheduled as soon as every CTA of this grid got here (they run their prologue and block in wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int MAX_STAGE_LEVELS = 14;
 constexpr int MAX_FUSED = 6;          // stages one cooperative launch can chain (incl. the top stage)
 
@@ -313,17 +319,33 @@ __device__ __forceinline__ void publish_node(const StageArgs& a, size_t node, in
 
 // Unit upper triangular solve by one warp: lane i holds r_i and leaves with x_i.  U is packed by
 // columns with rows already divided by their diagonal entry; the diagonal slot holds 1 / U_ii.
+// Blocks of four columns: one round of shuffles brings the four right-hand sides of the block to
+// every lane, every lane solves the 4 x 4 unit triangle itself (its entries are broadcast reads)
+// and applies the four columns to its own row.  Per entry the subtractions happen in the same
+// order (descending column) as in a column-at-a-time substitution - bit-identical results - but
+// the dependent chain is one shuffle round + 4 complex FMAs per FOUR unknowns instead of one
+// shuffle round + one FMA per unknown (~1400 -> ~850 cycles for 32 unknowns).
 __device__ __forceinline__ cd unit_upper_solve(const cd* U, cd r, int lane) {
   r = r * U[tri_up_off(lane) + lane];
-  cd u[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) u[j] = U[tri_up_off(SB - 1 - j) + min(lane, SB - 1 - j)];
-#pragma unroll
-  for (int k = SB - 1; k >= 1; --k) {
-    const cd xk = shfl_cd(r, k);
-    const cd uk = u[(SB - 1 - k) & 3];
-    if (k >= 5) u[(SB - 1 - k) & 3] = U[tri_up_off(k - 4) + min(lane, k - 4)];
-    if (lane < k) cfms(r, uk, xk);
+  for (int kb = SB / 4 - 1; kb >= 0; --kb) {
+    const int c0 = 4 * kb;
+    const cd* k1 = U + tri_up_off(c0 + 1);
+    const cd* k2 = U + tri_up_off(c0 + 2);
+    const cd* k3 = U + tri_up_off(c0 + 3);
+    const int li = min(lane, c0);   // rows above the block use their own entries of the four columns
+    const cd w0 = U[tri_up_off(c0) + li], w1 = k1[li], w2 = k2[li], w3 = k3[li];
+    const cd u01 = k1[c0], u02 = k2[c0], u12 = k2[c0 + 1], u03 = k3[c0], u13 = k3[c0 + 1], u23 = k3[c0 + 2];
+    const cd a0 = shfl_cd(r, c0), a1 = shfl_cd(r, c0 + 1), a2 = shfl_cd(r, c0 + 2), x3 = shfl_cd(r, c0 + 3);
+    cd x2 = a2; cfms(x2, u23, x3);
+    cd x1 = a1; cfms(x1, u13, x3); cfms(x1, u12, x2);
+    cd x0 = a0; cfms(x0, u03, x3); cfms(x0, u02, x2); cfms(x0, u01, x1);
+    if (lane < c0) {
+      cfms(r, w3, x3); cfms(r, w2, x2); cfms(r, w1, x1); cfms(r, w0, x0);
+    } else if (lane < c0 + 4) {
+      const int j = lane - c0;
+      r = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
+    }
   }
   return r;
 }
@@ -536,8 +558,9 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArg
   const Ring rg{slots, bars, bars + ns, ns, GRAN};
   if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init_fence(); }
   __syncthreads();
+  pdl_launch_dependents();
   if (threadIdx.x >= NCW * 32) {
-    if (threadIdx.x == NCW * 32) {
+    if (threadIdx.x == NCW * 32) {   // the factor records are static: streamed before the dependency resolves
       Producer pr;
       pr.policy = gridDim.x > 148 ? l2_policy_evict_first() : l2_policy_evict_last();
       const int r0 = blockIdx.x * C;
@@ -545,6 +568,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArg
     }
     return;
   }
+  pdl_wait();
   RingPos pos{0, 0u};
   fwd_stage_body(a, blockIdx.x, rg, pos, buf0, buf1, part);
 }
@@ -563,6 +587,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
   const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
   if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
   __syncthreads();
+  pdl_launch_dependents();
   if (threadIdx.x >= NCW * 32) {
     if (threadIdx.x == NCW * 32) {
       Producer pr;
@@ -572,6 +597,7 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
     }
     return;
   }
+  pdl_wait();
   RingPos pos{0, 0u}, upos{0, 0u};
   bwd_stage_body(a, blockIdx.x, rg, pos, ur, upos, z, part);
 }
@@ -647,6 +673,275 @@ __global__ void __launch_bounds__(RING_THREADS) slu_fused_stage_kernel(const __g
     if (b >= a.nchunks) continue;
     bwd_stage_body(a, b, rg, pos, ur, upos, z, part);  // boundary unknowns: polled from the mailbox
     consumer_sync();
+  }
+}
+
+// ---- upper stages with RESIDENT factor records -----------------------------------------------
+// The levels above the first stage hold 312 pairs at G = 10 001 (20 MB of records): their cost is
+// not bytes but a chain of ~2 x 9 dependent pair steps plus the dense top system.  The version
+// above streams the records of a chunk through rings and lets CTA 0 take part in every stage, so
+// every pair step also waits for its ~66 KB to pass the SM's copy engine (>= 0.6 us per pair) and
+// runs all 8 warps + two CTA barriers per pair.  Here instead
+//   * every chunk of every stage and the top system get a CTA (SM) of their own: 79 + 20 + 5 + 2 + 1
+//     at G = 10 001, all co-resident; a chunk has at most three pairs (mu <= 2), whose records
+//     (<= 200 KB) are copied into shared memory ONCE, by bulk copies issued in the prologue - before
+//     griddepcontrol.wait, i.e. while the previous kernel of the solve is still running when the
+//     launch is programmatic - so no pair step ever waits for a copy;
+//   * a pair is worked on by four warps (thread = row r of an octet, column group q: 8 columns
+//     each, two shuffle rounds instead of a partial-sum exchange through shared memory), so the
+//     two pairs of a level run concurrently on the two halves of the CTA;
+//   * the U substitution is blocked by four columns (unit_upper_solve).
+// Hand-offs between CTAs are the same mailboxes as above.
+constexpr int UP_THREADS = 256;
+constexpr int UP_MAXPAIRS = 3;                              // mu <= 2: two pairs + one pair
+constexpr int UP_REC_ELEMS = UP_MAXPAIRS * PAIR_STRIDE;     // also fits one pair + the dense top record
+static_assert(PAIR_STRIDE + TOP_STRIDE <= UP_REC_ELEMS, "top CTA: one pair record + the dense top record");
+constexpr int UP_FWD_ELEMS = PR_E - PR_PERM;                // [perm | L11^-1 | M2]
+constexpr int UP_BWD_ELEMS = PR_U + TRI - PR_E;             // [E | F | U]
+
+struct UpperArgs {
+  int nst;                       // stages of this launch; the last one is the top stage
+  int cta0[MAX_FUSED + 1];       // first CTA of each stage
+  StageArgs st[MAX_FUSED];
+};
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+}
+__device__ __forceinline__ cd quad_sum(cd v) {   // over the four column groups: lanes l, l ^ 8, l ^ 16, l ^ 24
+  v.x += __shfl_xor_sync(0xffffffffu, v.x, 8);
+  v.y += __shfl_xor_sync(0xffffffffu, v.y, 8);
+  v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+  v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+  return v;
+}
+
+// forward sweep of one pair by 128 threads: out = (P s)_2 - M2 (P s)_1, g = L11^-1 (P s)_1
+__device__ __forceinline__ void up_pair_forward(const cd* rec, const cd* s, cd* out, cd* g, int t) {
+  const int lane = t & 31, q = lane >> 3, row = 8 * (t >> 5) + (lane & 7);
+  const uint8_t* perm = reinterpret_cast<const uint8_t*>(rec + PR_PERM);
+  const cd* L = rec + PR_L11I;
+  const cd* M = rec + PR_L21;
+  cd v1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v1[k] = s[perm[q + 4 * k]];
+  cd ga{0.0, 0.0}, gb{0.0, 0.0}, oa{0.0, 0.0}, ob{0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const int c = q + 4 * k, d = c + 4;
+    cfma(oa, M[c * SB + row], v1[k]);
+    cfma(ob, M[d * SB + row], v1[k + 1]);
+    if (c <= row) cfma(ga, L[tri_lo_off(c) + row - c], v1[k]);
+    if (d <= row) cfma(gb, L[tri_lo_off(d) + row - d], v1[k + 1]);
+  }
+  const cd gs = quad_sum(ga + gb), os = quad_sum(oa + ob);
+  if (q == 0) {
+    out[row] = s[perm[SB + row]] - os;
+    g[row] = gs;
+  }
+}
+
+// right-hand side of the back substitution of one pair by 128 threads: r = g - E z_left - F z_right
+__device__ __forceinline__ void up_pair_backward_rhs(const cd* rec, const cd* zl, const cd* zr, const cd* g,
+                                                     cd* r, int t) {
+  const int lane = t & 31, q = lane >> 3, row = 8 * (t >> 5) + (lane & 7);
+  const cd* E = rec + PR_E;
+  const cd* F = rec + PR_F;
+  cd ea{0.0, 0.0}, eb{0.0, 0.0}, fa{0.0, 0.0}, fb{0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const int c = q + 4 * k, d = c + 4;
+    cfma(ea, E[c * SB + row], zl[c]);
+    cfma(eb, E[d * SB + row], zl[d]);
+    cfma(fa, F[c * SB + row], zr[c]);
+    cfma(fb, F[d * SB + row], zr[d]);
+  }
+  const cd acc = quad_sum((ea + eb) + (fa + fb));
+  if (q == 0) r[row] = g[row] - acc;
+}
+
+// 64 x 64 unit upper triangular solve by one warp (rows lane and lane + 32), column-major with
+// leading dimension 64, diagonal slot = 1 / U_ii; blocked by four columns like unit_upper_solve
+__device__ __forceinline__ void unit_upper_solve64(const cd* U, cd& y0, cd& y1, int lane) {
+  y0 = y0 * U[lane * 64 + lane];
+  y1 = y1 * U[(lane + 32) * 64 + lane + 32];
+#pragma unroll 4
+  for (int kb = 15; kb >= 0; --kb) {
+    const int c0 = 4 * kb;
+    const bool hi = kb >= 8;
+    const cd* k0 = U + c0 * 64;
+    const cd* k1 = k0 + 64;
+    const cd* k2 = k0 + 128;
+    const cd* k3 = k0 + 192;
+    const cd u01 = k1[c0], u02 = k2[c0], u12 = k2[c0 + 1], u03 = k3[c0], u13 = k3[c0 + 1], u23 = k3[c0 + 2];
+    const cd src = hi ? y1 : y0;
+    const cd a0 = shfl_cd(src, c0 & 31), a1 = shfl_cd(src, (c0 + 1) & 31), a2 = shfl_cd(src, (c0 + 2) & 31),
+             x3 = shfl_cd(src, (c0 + 3) & 31);
+    cd x2 = a2; cfms(x2, u23, x3);
+    cd x1 = a1; cfms(x1, u13, x3); cfms(x1, u12, x2);
+    cd x0 = a0; cfms(x0, u03, x3); cfms(x0, u02, x2); cfms(x0, u01, x1);
+    if (hi || lane < c0) {
+      cfms(y0, k3[lane], x3); cfms(y0, k2[lane], x2); cfms(y0, k1[lane], x1); cfms(y0, k0[lane], x0);
+    } else if (lane < c0 + 4) {
+      const int j = lane - c0;
+      y0 = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
+    }
+    if (hi) {
+      const int i = lane + 32;
+      if (i < c0) {
+        cfms(y1, k3[i], x3); cfms(y1, k2[i], x2); cfms(y1, k1[i], x1); cfms(y1, k0[i], x0);
+      } else if (i < c0 + 4) {
+        const int j = i - c0;
+        y1 = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
+      }
+    }
+  }
+}
+
+// smem: [3 pair records | (top CTA) 1 pair record + dense top record][level rows 2 x 4 x 32][g 3 x 32]
+//       [z 5 x 32][r 2 x 32][t 64][partial sums 4 x 64][7 barriers]
+constexpr size_t UP_SMEM = sizeof(cd) * (UP_REC_ELEMS + 2 * 4 * SB + UP_MAXPAIRS * SB + 5 * SB + 2 * SB + 64 + 4 * 64) +
+                           sizeof(uint64_t) * (2 * UP_MAXPAIRS + 2);
+
+__global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_constant__ UpperArgs f) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemCursor sc{smem_raw};
+  cd* recs = sc.take<cd>(UP_REC_ELEMS);
+  cd* rows = sc.take<cd>(2 * 4 * SB);
+  cd* gbuf = sc.take<cd>(UP_MAXPAIRS * SB);
+  cd* z = sc.take<cd>(5 * SB);
+  cd* rbuf = sc.take<cd>(2 * SB);
+  cd* tvec = sc.take<cd>(64);
+  cd* part = sc.take<cd>(4 * 64);
+  uint64_t* bars = sc.take<uint64_t>(2 * UP_MAXPAIRS + 2);   // [2p] forward part of pair p, [2p + 1] backward part, [6] top record
+  const int tid = threadIdx.x, lane = tid & 31, b = blockIdx.x;
+  int s = 0;
+  while (s + 1 < f.nst && b >= f.cta0[s + 1]) ++s;
+  const StageArgs& a = f.st[s];
+  const bool top = s == f.nst - 1;
+  const int chunk = b - f.cta0[s];
+  const int r0 = top ? 0 : chunk << a.mu;
+  const int cnt = top ? a.m0 : min(1 << a.mu, a.m0 - r0);
+  // pairs of the chunk, level by level: slot0[lam] = first record slot of level lam
+  int slot0[3] = {0, 0, 0}, npair[2] = {0, 0};
+  for (int lam = 0; lam < a.mu; ++lam) {
+    npair[lam] = ((cnt + (1 << lam) - 1) >> lam) / 2;
+    slot0[lam + 1] = slot0[lam] + npair[lam];
+  }
+  // ---- prologue: every record this CTA will ever use -> shared memory (static data: no dependence on
+  // the kernels before this one)
+  if (tid == 0) {
+    for (int i = 0; i < 2 * UP_MAXPAIRS + 1; ++i) mbar_init(&bars[i], 1);
+    ring_init_fence();
+    const uint64_t keep = l2_policy_evict_last();
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int step = 0; step < a.mu; ++step) {
+        const int lam = pass == 0 ? step : a.mu - 1 - step;   // order of use
+        const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
+        for (int i = 0; i < npair[lam]; ++i) {
+          const int p = slot0[lam] + i;
+          const cd* rec = a.pairs + (pair0 + i) * PAIR_STRIDE;
+          const int off = pass == 0 ? PR_PERM : PR_E;
+          const uint32_t bytes = static_cast<uint32_t>(sizeof(cd) * (pass == 0 ? UP_FWD_ELEMS : UP_BWD_ELEMS));
+          mbar_expect_tx(&bars[2 * p + pass], bytes);
+          bulk_g2s_hint(recs + p * PAIR_STRIDE + off, rec + off, bytes, &bars[2 * p + pass], keep);
+        }
+      }
+      if (pass == 0 && top) {
+        const uint32_t bytes = static_cast<uint32_t>(sizeof(cd) * TOP_STRIDE);
+        mbar_expect_tx(&bars[2 * UP_MAXPAIRS], bytes);
+        bulk_g2s_hint(recs + PAIR_STRIDE, a.top, bytes, &bars[2 * UP_MAXPAIRS], keep);
+      }
+    }
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();   // everything below reads what earlier kernels wrote
+  // ---- input rows
+  if (tid < cnt * SB) {
+    const cd* src = a.fin + static_cast<size_t>(r0) * SB + tid;
+    rows[tid] = a.poll_in ? mbox_poll(src) : ldcg_cd(src);
+  }
+  __syncthreads();
+  const int grp = tid >> 7, t = tid & 127;
+  cd* cur = rows;
+  cd* nxt = rows + 4 * SB;
+  // ---- forward: the pairs of a level side by side
+  for (int lam = 0; lam < a.mu; ++lam) {
+    const int ml = (cnt + (1 << lam) - 1) >> lam, np = npair[lam];
+    if (grp < np) {
+      const int p = slot0[lam] + grp;
+      mbar_wait(&bars[2 * p], 0u);
+      up_pair_forward(recs + p * PAIR_STRIDE, cur + 2 * grp * SB, nxt + grp * SB, gbuf + p * SB, t);
+    }
+    if ((ml & 1) && tid >= UP_THREADS - 32) nxt[np * SB + lane] = cur[2 * np * SB + lane];   // odd row: carried up
+    __syncthreads();
+    cd* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (!top) {
+    if (tid < SB) {
+      if (a.fout_clear != nullptr) a.fout_clear[static_cast<size_t>(chunk) * SB + tid] = mbox_empty();
+      a.fout[static_cast<size_t>(chunk) * SB + tid] = cur[tid];
+    }
+    // boundary unknowns of the chunk
+    if (tid < 2 * SB) {
+      const bool right = tid >= SB;
+      const size_t idx = unknown_index(a, right ? r0 + cnt : r0) * SB + lane;
+      z[(right ? cnt * SB : 0) + lane] = a.poll_z ? mbox_poll(a.zbox + idx) : ldcg_cd(a.xv + idx);
+    }
+  } else {
+    // ---- dense top system [boundary row of node 0 ; last reduced row ; boundary row of node n_pad - 1]
+    const cd* toprec = recs + PAIR_STRIDE;
+    if (tid < 64) {
+      cd v{0.0, 0.0};
+      if (tid < 16) v = a.b[tid];
+      else if (tid < 48) v = cur[tid - 16];
+      else if (a.n_pad - 1 < a.n) v = a.b[static_cast<size_t>(a.n_pad - 1) * 16 + tid - 48];
+      tvec[tid] = v;
+    }
+    mbar_wait(&bars[2 * UP_MAXPAIRS], 0u);
+    __syncthreads();
+    {   // y = Linv (P t): thread = (row, 16 columns)
+      const uint8_t* perm = reinterpret_cast<const uint8_t*>(toprec);
+      const cd* Linv = toprec + TOP_LINV;
+      const int row = tid & 63, cg = tid >> 6;
+      cd p0{0.0, 0.0}, p1{0.0, 0.0};
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        cfma(p0, Linv[(cg * 16 + c) * 64 + row], tvec[perm[cg * 16 + c]]);
+        cfma(p1, Linv[(cg * 16 + c + 1) * 64 + row], tvec[perm[cg * 16 + c + 1]]);
+      }
+      part[cg * 64 + row] = p0 + p1;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      cd y0 = (part[lane] + part[64 + lane]) + (part[128 + lane] + part[192 + lane]);
+      cd y1 = (part[32 + lane] + part[96 + lane]) + (part[160 + lane] + part[224 + lane]);
+      unit_upper_solve64(toprec + TOP_U, y0, y1, lane);
+      z[lane] = y0;
+      publish_node(a, 0, lane, y0);
+      z[cnt * SB + lane] = y1;
+      publish_node(a, static_cast<size_t>(a.K - 1), lane, y1);
+    }
+  }
+  __syncthreads();
+  // ---- backward: z = U^-1 (g - E z_left - F z_right), upper level first, pairs of a level side by side
+  for (int lam = a.mu - 1; lam >= 0; --lam) {
+    const int st = 1 << lam, np = npair[lam];
+    if (grp < np) {
+      const int p = slot0[lam] + grp;
+      const cd* rec = recs + p * PAIR_STRIDE;
+      const int ql = 2 * grp * st, qr = min(ql + 2 * st, cnt), qm = ql + st;
+      mbar_wait(&bars[2 * p + 1], 0u);
+      up_pair_backward_rhs(rec, z + ql * SB, z + qr * SB, gbuf + p * SB, rbuf + grp * SB, t);
+      group_sync(grp);
+      if (t < 32) {
+        const cd x = unit_upper_solve(rec + PR_U, rbuf[grp * SB + lane], lane);
+        z[qm * SB + lane] = x;
+        publish_node(a, unknown_index(a, r0 + qm), lane, x);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -1184,16 +1479,17 @@ constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + NBF * 64) + sizeof(int) *
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
-  static bool done = false;
-  if (done) return;
+  static PerDeviceOnce once;
+  once.run([] {
   const int big = static_cast<int>(SMEM_PER_CTA_1);
   CUDA_CHECK(cudaFuncSetAttribute(slu_fwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_bwd_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_fused_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  done = true;
+  });
 }
 
 }  // namespace
@@ -1248,12 +1544,7 @@ static double stage_algo_bytes(const SluPlan& plan, int s, double per_point) {
 // first stage (>= 1) from which the rest of the solve runs as one cooperative launch, or the
 // index of the top stage when there is nothing to fuse
 static int first_fused_stage(const SluPlan& plan) {
-  static const int sm_count = [] {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
+  const int sm_count = device_sm_count();
   static const bool enabled = [] { const char* e = std::getenv("LGPU_SLU_FUSE"); return !(e && e[0] == '0'); }();
   const int ns = static_cast<int>(plan.stages.size());
   if (!enabled || ns < 3) return ns - 1;
@@ -1262,30 +1553,71 @@ static int first_fused_stage(const SluPlan& plan) {
   return sf;
 }
 
+// Same for the resident-record kernel (slu_upper_kernel): every chunk of every fused stage gets its own
+// CTA, so the CTAs of ALL fused stages must be co-resident; chunks of at most three pairs (mu <= 2), a
+// top stage of at most two rows.  -1: not applicable to this plan.
+static int first_upper_stage(const SluPlan& plan) {
+  static const bool enabled = [] { const char* e = std::getenv("LGPU_SLU_UPPER"); return !(e && e[0] == '0'); }();
+  const int ns = static_cast<int>(plan.stages.size());
+  if (!enabled || ns < 2 || plan.top_size != 64) return -1;
+  const SluStage& top = plan.stages[ns - 1];
+  if (top.m0 > 2 || top.mu > 1) return -1;
+  const int sm_count = device_sm_count();
+  int sf = ns - 1, ctas = 1;
+  while (sf > 1 && ns - (sf - 1) <= MAX_FUSED && plan.stages[sf - 1].mu <= 2 &&
+         ctas + plan.stages[sf - 1].nchunks <= sm_count) {
+    --sf;
+    ctas += plan.stages[sf].nchunks;
+  }
+  return sf;
+}
+
+// Programmatic dependent launch of the solve's kernels: a kernel may start while its predecessor on
+// the stream is still running; it copies its first factor records (static data) and then blocks in
+// griddepcontrol.wait until the predecessor has completed.
+static bool pdl_enabled() {
+  static const bool on = [] { const char* e = std::getenv("LGPU_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... Args>
+static void launch_pdl(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
+}
+
 void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
                LaunchLog* log) {
   configure_kernels();
   const int ns = static_cast<int>(plan.stages.size());
-  const int sf = first_fused_stage(plan);
+  const int su = first_upper_stage(plan);
+  const int sf = su >= 0 ? su : first_fused_stage(plan);
   cd* xv = plan.n_pad == plan.n ? x : d.xpad;
   for (int s = 0; s < sf; ++s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv);
     log->begin(s == 0 ? LK_FWD0 : LK_FWD, stage_algo_bytes(plan, s, 7936.0));
     const RingShape sh = fwd_shape(a);
-    slu_fwd_stage_kernel<<<a.nchunks, RING_THREADS, sh.bytes, stream>>>(a, sh.ns);
+    launch_pdl(slu_fwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns);
     log->end();
   }
   double top_bytes = stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2;
-  if (sf == ns - 1) {
+  if (su < 0 && sf == ns - 1) {
     const StageArgs a = make_stage_args(plan, d, ns - 1, b, xv);
     log->begin(LK_TOP, top_bytes);
     const RingShape sh = bwd_shape(a, true);
     slu_top_stage_kernel<<<1, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
     log->end();
   } else {
-    FusedArgs f{};
-    f.nst = ns - sf;
-    f.cmax = 1;
+    // stage arguments shared by the two fused kernels: mailboxes between the CTAs of the launch
+    StageArgs fst[MAX_FUSED];
     int mu_max = 0;
     const unsigned long long parity = (*d.epoch + 1) & 1ull;   // of the solve being launched
     const size_t half = slu_mbox_half(plan);
@@ -1293,7 +1625,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     cd* box_other = d.mbox + (1 - parity) * half;
     const size_t zoff = plan.rhs_vecs * SB;
     for (int s = sf; s < ns; ++s) {
-      StageArgs& a = f.st[s - sf];
+      StageArgs& a = fst[s - sf];
       a = make_stage_args(plan, d, s, b, xv);
       if (s > sf) {            // input rows come from another CTA of this launch
         a.fin = box + plan.stages[s].off_fin * SB;
@@ -1309,23 +1641,39 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
       mu_max = std::max(mu_max, plan.stages[s].mu);
       if (s < ns - 1) top_bytes += stage_algo_bytes(plan, s, 24064.0);
     }
-    f.cmax = 1 << mu_max;
-    StageArgs widest = f.st[0];
-    widest.mu = mu_max;
-    const RingShape sh = bwd_shape(widest, true);
-    f.ns = sh.ns; f.nu = sh.nu;
     ++*d.epoch;
-    void* args[] = {&f};
     log->begin(LK_TOP, top_bytes);
-    CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(slu_fused_stage_kernel), dim3(f.st[0].nchunks),
-                                           dim3(RING_THREADS), args, sh.bytes, stream));
+    if (su >= 0) {
+      UpperArgs u{};
+      u.nst = ns - sf;
+      int ctas = 0;
+      for (int i = 0; i < u.nst; ++i) {
+        u.st[i] = fst[i];
+        u.cta0[i] = ctas;
+        ctas += i == u.nst - 1 ? 1 : fst[i].nchunks;
+      }
+      u.cta0[u.nst] = ctas;
+      launch_pdl(slu_upper_kernel, dim3(ctas), dim3(UP_THREADS), UP_SMEM, stream, u);
+    } else {
+      FusedArgs f{};
+      f.nst = ns - sf;
+      for (int i = 0; i < f.nst; ++i) f.st[i] = fst[i];
+      f.cmax = 1 << mu_max;
+      StageArgs widest = f.st[0];
+      widest.mu = mu_max;
+      const RingShape sh = bwd_shape(widest, true);
+      f.ns = sh.ns; f.nu = sh.nu;
+      void* args[] = {&f};
+      CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(slu_fused_stage_kernel), dim3(f.st[0].nchunks),
+                                             dim3(RING_THREADS), args, sh.bytes, stream));
+    }
     log->end();
   }
   for (int s = sf - 1; s >= 0; --s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv);
     log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
     const RingShape sh = bwd_shape(a, false);
-    slu_bwd_stage_kernel<<<a.nchunks, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
+    launch_pdl(slu_bwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns, sh.nu);
     log->end();
   }
   log->launches += 2 * sf + 1;

@@ -241,7 +241,8 @@ def create_datfile(path, settings: Settings, base_grid: np.ndarray, gauss_grid: 
             w.ls(name)
             w.d(info.units.get(name, float("nan")))
         # ---- write_physics_info
-        w.d(settings.gamma)
+        # set_incompressible overwrites gamma (src/settings/mod_physics_settings.f08:90-94)
+        w.d(1.0e12 if settings.incompressible else settings.gamma)
         w.b(settings.incompressible)
         w.b(settings.flow)
         w.b(settings.cooling)
@@ -253,7 +254,8 @@ def create_datfile(path, settings: Settings, base_grid: np.ndarray, gauss_grid: 
         w.b(settings.viscosity)
         w.b(settings.viscous_heating)
         w.b(settings.conduction)
-        w.b(settings.conduction)                      # parallel conduction is on whenever conduction is
+        # conduction%is_enabled() = parallel .or. perpendicular (src/settings/mod_physics_settings.f08)
+        w.b(settings.conduction if settings.parallel_conduction is None else settings.parallel_conduction)
         w.b(info.fixed_tc_para)
         w.b(settings.perpendicular_conduction)
         w.b(info.fixed_tc_perp)
