@@ -337,10 +337,16 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
 
   c->log.stream = c->stream;
   CUDA_CHECK(cudaEventRecord(c->ev0, c->stream));
+  {   // sampled fields + grids in, two block-tridiagonal matrices out
+    int nf = 0;
+    for (int f = 0; f < NFIELD; ++f) nf += fields.f[f] != nullptr;
+    c->log.begin(LK_ASSEMBLE, 8.0 * nf * 4.0 * (G - 1) + 8.0 * (G + 4.0 * (G - 1)) + 2.0 * 12288.0 * G);
+  }
   launch_assemble(p, de, fields, d_grid, d_gauss, c->A.p, c->B.p, c->masks.p, c->stream);
   launch_boundaries(p, dn, fields, d_grid, d_gauss, c->A.p, c->B.p, c->masks.p, c->natmasks.p,
                     c->d_plan_i32.p + o_el, static_cast<int>(essl.size()), c->d_plan_i32.p + o_er,
                     static_cast<int>(essr.size()), c->stream);
+  c->log.end();
   c->log.launches += 2;
   CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
   CUDA_CHECK(cudaEventSynchronize(c->ev1));

@@ -810,7 +810,8 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   *work.gbar_count += 2ull * grid;
   a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
   const size_t smem = cgs2_smem(ncopy, nstages, tiles_max);
-  log->begin(LK_CGS2, 16.0 * L.n * (3.0 * ncols + 4.0));
+  // one orthogonalisation at basis size j = two passes, 2 (j + 2) 256 G bytes
+  log->begin(LK_CGS2, 16.0 * L.n * (2.0 * ncols + 4.0));
   switch (exact ? cpg : 0) {
     case 5: launch_cgs2<5>(a, grid, smem, stream); break;
     case 6: launch_cgs2<6>(a, grid, smem, stream); break;
