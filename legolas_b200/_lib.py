@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblegolas_b200.so")
+LIB_PATH = os.environ.get("LGPU_LIB") or os.path.join(HERE, "liblegolas_b200.so")
 
 N_FIELDS = 38
 

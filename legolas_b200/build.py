@@ -11,7 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "liblegolas_b200.so")
+# LGPU_LIB: path of a debugging variant (e.g. built with LGPU_NVCC_EXTRA=-DLGPU_TRACE); the product library is the default
+LIB = os.environ.get("LGPU_LIB") or os.path.join(HERE, "liblegolas_b200.so")
 SOURCES = ["api.cu", "assemble.cu", "slu.cu", "arnoldi.cu", "bsparse.cu", "efs.cu"]
 HEADERS = ["common.cuh", "assemble.cuh", "slu.cuh", "arnoldi.cuh", "bsparse.cuh", "efs.cuh", "iram.hpp", "dense_host.hpp",
            "terms.def", os.path.join("..", "..", "include", "legolas_b200.h")]
@@ -41,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if "LGPU_LIB" not in os.environ else "build_" + os.path.basename(LIB).replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []

@@ -87,6 +87,29 @@ __device__ __forceinline__ int tri_up_off(int k) { return (k * (k + 1)) / 2; }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Optional timeline of the solve kernels (-DLGPU_TRACE, scripts/solve_trace.py): thread 0 of every CTA stores
+// %globaltimer at phase boundaries.  Never compiled into the product library.
+#ifdef LGPU_TRACE
+constexpr int TRACE_SLOTS = 16, TRACE_CTAS = 512;
+__device__ unsigned long long g_trace[3][TRACE_CTAS * TRACE_SLOTS];   // [0] forward stage 0, [1] upper, [2] backward stage 0
+__device__ __forceinline__ void trace_mark(int which, int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < TRACE_CTAS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[which][blockIdx.x * TRACE_SLOTS + slot] = t;
+  }
+}
+__device__ __forceinline__ void trace_value(int which, int slot, unsigned long long v) {
+  if (threadIdx.x == 0 && blockIdx.x < TRACE_CTAS) g_trace[which][blockIdx.x * TRACE_SLOTS + slot] = v;
+}
+__device__ __forceinline__ unsigned trace_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define TRACE_MARK(w, s) trace_mark(w, s)
+#define TRACE_VALUE(w, s, v) trace_value(w, s, v)
+#else
+#define TRACE_MARK(w, s)
+#define TRACE_VALUE(w, s, v)
+#endif
+
 constexpr int MAX_STAGE_LEVELS = 14;
 constexpr int MAX_FUSED = 6;          // stages one cooperative launch can chain (incl. the top stage)
 
@@ -574,6 +597,8 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArg
   cd* part = sc.take<cd>(2 * NCW * SB);
   uint64_t* bars = sc.take<uint64_t>(2 * ns);
   const Ring rg{slots, bars, bars + ns, ns, GRAN};
+  TRACE_MARK(0, 0);
+  TRACE_VALUE(0, 15, trace_smid());
   if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init_fence(); }
   __syncthreads();
   pdl_launch_dependents();
@@ -587,8 +612,10 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_fwd_stage_kernel(StageArg
     return;
   }
   pdl_wait();
+  TRACE_MARK(0, 1);
   RingPos pos{0, 0u};
   fwd_stage_body(a, blockIdx.x, rg, pos, buf0, buf1, part);
+  TRACE_MARK(0, 2);
 }
 
 // smem: [ns slots][nu U slots][z (C + 1) x 32][part][barriers]
@@ -603,6 +630,8 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
   uint64_t* bars = sc.take<uint64_t>(2 * (ns + nu));
   const Ring rg{slots, bars, bars + ns, ns, GRAN};
   const Ring ur{uslots, bars + 2 * ns, bars + 2 * ns + nu, nu, TRI};
+  TRACE_MARK(2, 0);
+  TRACE_VALUE(2, 15, trace_smid());
   if (threadIdx.x == 0) { ring_init(rg, NCW); ring_init(ur, 1); ring_init_fence(); }
   __syncthreads();
   pdl_launch_dependents();
@@ -616,8 +645,10 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
     return;
   }
   pdl_wait();
+  TRACE_MARK(2, 1);
   RingPos pos{0, 0u}, upos{0, 0u};
   bwd_stage_body(a, blockIdx.x, rg, pos, ur, upos, z, part);
+  TRACE_MARK(2, 2);
 }
 
 // The narrow upper stages and the top system in ONE cooperative launch (grid = chunks of the first
@@ -833,8 +864,10 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   cd* part = sc.take<cd>(4 * 64);
   uint64_t* bars = sc.take<uint64_t>(2 * UP_MAXPAIRS + 2);   // [2p] forward part of pair p, [2p + 1] backward part, [6] top record
   const int tid = threadIdx.x, lane = tid & 31, b = blockIdx.x;
+  TRACE_MARK(1, 0);
   int s = 0;
   while (s + 1 < f.nst && b >= f.cta0[s + 1]) ++s;
+  TRACE_VALUE(1, 15, (static_cast<unsigned long long>(s) << 32) | trace_smid());
   const StageArgs& a = f.st[s];
   const bool top = s == f.nst - 1;
   const int chunk = b - f.cta0[s];
@@ -873,14 +906,17 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
     }
   }
   __syncthreads();
+  TRACE_MARK(1, 1);
   pdl_launch_dependents();
   pdl_wait();   // everything below reads what earlier kernels wrote
+  TRACE_MARK(1, 2);
   // ---- input rows
   if (tid < cnt * SB) {
     const cd* src = a.fin + static_cast<size_t>(r0) * SB + tid;
     rows[tid] = a.poll_in ? mbox_poll(src) : ldcg_cd(src);
   }
   __syncthreads();
+  TRACE_MARK(1, 3);
   const int grp = tid >> 7, t = tid & 127;
   cd* cur = rows;
   cd* nxt = rows + 4 * SB;
@@ -896,6 +932,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
     __syncthreads();
     cd* tmp = cur; cur = nxt; nxt = tmp;
   }
+  TRACE_MARK(1, 4);
   if (!top) {
     if (tid < SB) {
       if (a.fout_clear != nullptr) a.fout_clear[static_cast<size_t>(chunk) * SB + tid] = mbox_empty();
@@ -932,6 +969,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       part[cg * 64 + row] = p0 + p1;
     }
     __syncthreads();
+    TRACE_MARK(1, 13);
     if (tid < 32) {
       cd y0 = (part[lane] + part[64 + lane]) + (part[128 + lane] + part[192 + lane]);
       cd y1 = (part[32 + lane] + part[96 + lane]) + (part[160 + lane] + part[224 + lane]);
@@ -940,9 +978,11 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       publish_node(a, 0, lane, y0);
       z[cnt * SB + lane] = y1;
       publish_node(a, static_cast<size_t>(a.K - 1), lane, y1);
+      TRACE_MARK(1, 14);
     }
   }
   __syncthreads();
+  TRACE_MARK(1, 5);
   // ---- backward: z = U^-1 (g - E z_left - F z_right), upper level first, pairs of a level side by side
   for (int lam = a.mu - 1; lam >= 0; --lam) {
     const int st = 1 << lam, np = npair[lam];
@@ -951,15 +991,19 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       const cd* rec = recs + p * PAIR_STRIDE;
       const int ql = 2 * grp * st, qr = min(ql + 2 * st, cnt), qm = ql + st;
       mbar_wait(&bars[2 * p + 1], 0u);
+      if (lam == a.mu - 1) TRACE_MARK(1, 10);
       up_pair_backward_rhs(rec, z + ql * SB, z + qr * SB, gbuf + p * SB, rbuf + grp * SB, t);
       group_sync(grp);
+      if (lam == a.mu - 1) TRACE_MARK(1, 11);
       if (t < 32) {
         const cd x = unit_upper_solve(rec + PR_U, rbuf[grp * SB + lane], lane);
         z[qm * SB + lane] = x;
         publish_node(a, unknown_index(a, r0 + qm), lane, x);
       }
+      if (lam == a.mu - 1) TRACE_MARK(1, 12);
     }
     __syncthreads();
+    TRACE_MARK(1, 6 + (a.mu - 1 - lam));
   }
 }
 
@@ -1701,6 +1745,13 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
   }
   CUDA_CHECK(cudaGetLastError());
 }
+
+#ifdef LGPU_TRACE
+extern "C" int lgpu_debug_solve_trace(int which, unsigned long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * TRACE_CTAS * TRACE_SLOTS,
+                                               sizeof(unsigned long long) * TRACE_CTAS * TRACE_SLOTS * which));
+}
+#endif
 
 static inline int use_a_count(cd v) { return (v.x != 0.0 || v.y != 0.0) ? 1 : 0; }
 

@@ -13,6 +13,12 @@ Follows (reference file:line):
   kelvin_helmholtz_cd ....... src/equilibria/smod_equil_kelvin_helmholtz_cd.f08:32-98
   MRI_accretion ............. src/equilibria/smod_equil_MRI_accretion.f08:36-133
   couette_flow .............. src/equilibria/smod_equil_couette_flow.f08:25-82
+  resistive_homo ............ src/equilibria/smod_equil_resistive_homo.f08:26-67
+  taylor_couette ............ src/equilibria/smod_equil_taylor_couette.f08:31-107
+  rotating_plasma_cylinder .. src/equilibria/smod_equil_rotating_plasma_cylinder.f08:29-120
+  RTI_theta_pinch ........... src/equilibria/smod_equil_RTI_theta_pinch.f08:33-119
+  harris_sheet .............. src/equilibria/smod_equil_harris_sheet.f08:26-128
+  Hall / inertia factors .... src/physics/mod_hall.f08:45-84
   on-axis grid shift ........ src/settings/mod_grid_settings.f08:112-138
   units ..................... src/settings/mod_units.f08:161-211, src/mod_physical_constants.f08
   resistivity ............... src/physics/mod_resistivity.f08:49-120
@@ -33,6 +39,8 @@ COULOMB_LOG = 22.0
 MP_CGS = 1.672621777e-24
 KB_CGS = 1.3806488e-16
 MU0_CGS = 4.0 * DPI
+ME_CGS = 9.1094e-28          # src/mod_physical_constants.f08:25
+EC_CGS = 4.8032e-10          # src/mod_physical_constants.f08:29
 TC_PF_KAPPA_PARA = 1.8e-5
 TC_PF_KAPPA_PERP = 8.2e-13
 
@@ -46,15 +54,19 @@ class Units:
     """units_t set from temperature (mod_units.f08:118-134,161-211)."""
 
     def __init__(self, unit_length=1.0e9, unit_magneticfield=10.0, unit_temperature=1.0e6,
-                 mean_molecular_weight=0.5):
+                 mean_molecular_weight=0.5, unit_density=None):
         self.unit_length = unit_length
         self.unit_magneticfield = unit_magneticfield
-        self.unit_temperature = unit_temperature
         self.mean_molecular_weight = mean_molecular_weight
         self.unit_pressure = unit_magneticfield**2 / MU0_CGS
-        self.unit_density = (
-            mean_molecular_weight * self.unit_pressure * MP_CGS / (KB_CGS * unit_temperature)
-        )
+        if unit_density is not None:   # set_units_from_density (mod_units.f08:96-115,176-186)
+            self.unit_density = unit_density
+            unit_temperature = mean_molecular_weight * self.unit_pressure * MP_CGS / (KB_CGS * unit_density)
+        else:
+            self.unit_density = (
+                mean_molecular_weight * self.unit_pressure * MP_CGS / (KB_CGS * unit_temperature)
+            )
+        self.unit_temperature = unit_temperature
         self.unit_numberdensity = self.unit_density / MP_CGS
         self.unit_velocity = unit_magneticfield / np.sqrt(MU0_CGS * self.unit_density)
         self.unit_mass = self.unit_density * unit_length**3
@@ -117,14 +129,142 @@ def dtcparadT(T0, units: Units):
 
 
 # --------------------------------------------------------------------- equilibria
+def hall_factors(units: Units, inertia: bool):
+    """mod_hall.f08:45-84 without drop-off profiles: (hallfactor, inertiafactor)."""
+    hf = (MP_CGS * units.unit_velocity) / (EC_CGS * units.unit_length * units.unit_magneticfield)
+    inf = (MP_CGS * ME_CGS * units.unit_velocity**2
+           / (EC_CGS * units.unit_length * units.unit_magneticfield) ** 2) if inertia else 0.0
+    return hf, inf
+
+
 def adiabatic_homo_eq(gridpts=51, k2=0.0, k3=DPI, cte_rho0=1.0, cte_T0=1.0, cte_B02=0.0,
-                      cte_B03=1.0, nodes=GAUSS_NODES, **overrides):
+                      cte_B03=1.0, x_start=0.0, x_end=1.0, units: Units | None = None, nodes=GAUSS_NODES,
+                      **overrides):
+    """With ``hall=True`` (and ``electron_inertia``) in the overrides this is the reference's uniform Hall case
+    (tests/regression_tests/test_uni_hall_adiabatic.py:9-31, test_uni_hall_elecinertia.py:9-29)."""
     s = Settings(gridpts=gridpts, geometry="Cartesian", k2=k2, k3=k3, **overrides)
-    grid, xg = _grid(s.geometry, 0.0, 1.0, gridpts, nodes)
+    grid, xg = _grid(s.geometry, x_start, x_end, gridpts, nodes)
     one = np.ones_like(xg)
     fields = {"rho0": cte_rho0 * one, "T0": cte_T0 * one, "B02": cte_B02 * one,
               "B03": cte_B03 * one}
+    if s.hall:
+        hf, inf = hall_factors(units or Units(), s.electron_inertia)
+        fields["hallfactor"] = hf * one
+        if s.electron_inertia:
+            fields["inertiafactor"] = inf * one
     return s, grid, xg, fields
+
+
+HALL_UNITS = dict(unit_length=7.534209349981049e-9, unit_magneticfield=10.0, unit_density=1.7e-14,
+                  mean_molecular_weight=1.0)   # test_uni_hall_adiabatic.py:25-30
+
+
+def uni_hall_eq(gridpts=51, inertia=False, k=DPI, nodes=GAUSS_NODES, **overrides):
+    """Uniform medium with Hall (and electron inertia) terms on [0, 1000]: k = pi rounded to 14 digits per component
+    for the adiabatic case (test_uni_hall_adiabatic.py:14-15), k = 10 for the inertia case
+    (test_uni_hall_elecinertia.py:14-15), both at 30 degrees to B."""
+    if inertia:
+        k2, k3 = 10 * np.sin(np.pi / 6), 10 * np.cos(np.pi / 6)
+    else:
+        k2, k3 = round(np.pi * np.sin(np.pi / 6), 14), round(np.pi * np.cos(np.pi / 6), 14)
+    return adiabatic_homo_eq(gridpts=gridpts, k2=k2, k3=k3, x_start=0.0, x_end=1000.0, units=Units(**HALL_UNITS),
+                             nodes=nodes, hall=True, electron_inertia=inertia, electron_fraction=0.5, **overrides)
+
+
+def resistive_homo_eq(gridpts=51, k2=0.0, k3=1.0, beta=0.25, cte_rho0=1.0, cte_B02=0.0, cte_B03=1.0,
+                      eta=1.0e-3, nodes=GAUSS_NODES, **overrides):
+    s = Settings(gridpts=gridpts, geometry="Cartesian", resistivity=True, k2=k2, k3=k3, **overrides)
+    grid, xg = _grid(s.geometry, 0.0, 1.0, gridpts, nodes)
+    one = np.ones_like(xg)
+    B0 = np.sqrt(cte_B02**2 + cte_B03**2)
+    fields = {"rho0": cte_rho0 * one, "T0": beta * B0**2 / 2.0 * one, "B02": cte_B02 * one,
+              "B03": cte_B03 * one, "eta": eta * one}
+    return s, grid, xg, fields
+
+
+def taylor_couette_eq(gridpts=51, k2=0.0, k3=1.0, cte_rho0=1.0, alpha=1.0, beta=2.0, x_start=1.0, x_end=2.0,
+                      viscosity_value=1.0e-3, nodes=GAUSS_NODES, **overrides):
+    s = Settings(gridpts=gridpts, geometry="cylindrical", flow=True, coaxial=True, viscosity=True,
+                 viscosity_value=viscosity_value, k2=k2, k3=k3, **overrides)
+    grid, r = _grid(s.geometry, x_start, x_end, gridpts, nodes)
+    Rrat = x_start / x_end
+    A = (alpha * Rrat**2 - beta) / (Rrat**2 - 1.0)
+    B = x_start**2 * (alpha - beta) / (1.0 - Rrat**2)
+    Tstart = 0.5 * ((A * x_start) ** 2 + 4.0 * A * B * np.log(x_start) - (B / x_start) ** 2)
+    T0 = 0.5 * ((A * r) ** 2 + 4.0 * A * B * np.log(r) - (B / r) ** 2)
+    if not Tstart > 0.0:
+        T0 = 2.0 * abs(Tstart) + T0
+    v02 = A * r + B / r
+    fields = {"rho0": cte_rho0 * np.ones_like(r), "T0": T0, "dT0": v02**2 / r,
+              "v02": v02, "dv02": A - B / r**2, "ddv02": 2.0 * B / r**3}
+    return s, grid, r, fields
+
+
+def rotating_plasma_cylinder_eq(gridpts=51, k2=1.0, k3=0.0, p1=8.0, p2=0.0, p3=0.0, p4=1.0, p5=0.0, p6=0.0,
+                                cte_p0=0.1, cte_rho0=1.0, nodes=GAUSS_NODES, **overrides):
+    s = Settings(gridpts=gridpts, geometry="cylindrical", flow=True, k2=k2, k3=k3, **overrides)
+    grid, r = _grid(s.geometry, 0.0, 1.0, gridpts, nodes)
+    one = np.ones_like(r)
+    a21, a22, a3, b21, b22, b3 = p1, p2, p3, p4, p5, p6
+    rho0 = cte_rho0
+    fields = {
+        "rho0": rho0 * one,
+        "T0": (1.0 / rho0) * (cte_p0 + 0.5 * (a21**2 - 2.0 * b21**2) * r**2
+                              + (2.0 / 3.0) * (a21 * a22 - b21 * b22) * r**3
+                              + (1.0 / 4.0) * (a22**2 - b22**2) * r**4),
+        "dT0": (1.0 / rho0) * ((a21**2 - 2.0 * b21**2) * r + 2.0 * (a21 * a22 - b21 * b22) * r**2
+                               + (a22**2 - b22**2) * r**3),
+        "v02": a21 * r + a22 * r**2, "dv02": a21 + 2.0 * a22 * r, "v03": a3 * one,
+        "B02": b21 * r + b22 * r**2, "dB02": b21 + 2.0 * b22 * r, "B03": b3 * one,
+    }
+    return s, grid, r, fields
+
+
+def rti_theta_pinch_eq(gridpts=51, k2=1.0, k3=0.0, cte_rho0=1.0, alpha=2.0, delta=1.0 / 6.0, r0=0.0,
+                       nodes=GAUSS_NODES, **overrides):
+    s = Settings(gridpts=gridpts, geometry="cylindrical", flow=True, k2=k2, k3=k3, **overrides)
+    grid, r = _grid(s.geometry, 0.0, 1.0, gridpts, nodes)
+    width = grid[-1] - grid[0]          # after the on-axis shift of the grid start
+    cte_p0 = 0.5 * (1.0 - delta) ** 2
+    B_inf = width * np.sqrt(cte_rho0)
+    bigO = alpha * np.sqrt(2.0 * delta * (1.0 - delta))
+    x = r / width
+    fx = alpha**2 * (x**2 - r0**2)
+    dfx = alpha**2 * 2.0 * x / width
+    fields = {
+        "rho0": cte_rho0 / np.cosh(fx) ** 2,
+        "drho0": -2.0 * cte_rho0 * dfx * np.tanh(fx) / np.cosh(fx) ** 2,
+        "T0": cte_p0 / cte_rho0 * np.ones_like(r),
+        "v02": bigO * r, "dv02": bigO * np.ones_like(r),
+        "B03": B_inf * (delta + (1.0 - delta) * np.tanh(fx)),
+        "dB03": B_inf * (1.0 - delta) * dfx / np.cosh(fx) ** 2,
+    }
+    return s, grid, r, fields
+
+
+def harris_sheet_eq(gridpts=51, k2=0.155, k3=0.01, alpha=1.0, cte_rho0=1.0, cte_B02=1.0, cte_B03=5.0,
+                    eta=1.0e-4, nodes=GAUSS_NODES, **overrides):
+    """The reference's Hall regression case (tests/regression_tests/test_hall_harris_sheet.py:8-33): resistive,
+    Hall, incompressible, eq_bool = .false. branch of the equilibrium."""
+    kw = dict(resistivity=True, hall=True, electron_fraction=0.5, incompressible=True)
+    kw.update(overrides)
+    s = Settings(gridpts=gridpts, geometry="Cartesian", k2=k2, k3=k3, **kw)
+    grid, x = _grid(s.geometry, -15.0, 15.0, gridpts, nodes)
+    one = np.ones_like(x)
+    B02 = cte_B02 * np.tanh(x / alpha)
+    B03 = cte_B03 * one
+    B0 = np.sqrt(B02**2 + B03**2)
+    fields = {
+        "rho0": cte_rho0 * one,
+        "T0": (cte_B03**2 + cte_B02**2 - B0**2) / (2.0 * cte_rho0),
+        "dT0": -cte_B02**2 * np.sinh(x / alpha) / (alpha * cte_rho0 * np.cosh(x / alpha) ** 3),
+        "B02": B02, "dB02": cte_B02 / (alpha * np.cosh(x / alpha) ** 2),
+        "ddB02": -2.0 * cte_B02 * np.sinh(x / alpha) / (alpha**2 * np.cosh(x / alpha) ** 3),
+        "B03": B03, "eta": eta * one,
+    }
+    if s.hall:
+        fields["hallfactor"] = hall_factors(Units(**HALL_UNITS), False)[0] * one
+    return s, grid, x, fields
 
 
 def couette_flow_eq(gridpts=51, k2=0.0, k3=1.0, cte_rho0=1.0, cte_T0=1.0, cte_v02=0.0, cte_v03=1.0,
@@ -284,4 +424,10 @@ EQUILIBRIA = {
     "kelvin_helmholtz_cd": kelvin_helmholtz_cd_eq,
     "MRI_accretion": mri_accretion_eq,
     "couette_flow": couette_flow_eq,
+    "resistive_homo": resistive_homo_eq,
+    "taylor_couette": taylor_couette_eq,
+    "rotating_plasma_cylinder": rotating_plasma_cylinder_eq,
+    "RTI_theta_pinch": rti_theta_pinch_eq,
+    "harris_sheet": harris_sheet_eq,
+    "uni_hall": uni_hall_eq,
 }

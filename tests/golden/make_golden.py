@@ -34,6 +34,18 @@ FILES = {
     "kh_cd_QR": "regression_tests/baseline/BASE_kelvin_helmholtz_current_driven_QR_k2_-1_k3_pi.dat",
     # the reference's hydrodynamic ("hd", 5-variable state vector) regression case
     "couette_HD_QR": "regression_tests/baseline/BASE_couette_HD_QR_k2_0_k3_1.dat",
+    # optional-physics term groups: Hall, electron inertia, viscosity, viscous heating, resistivity, flow
+    "uni_adiab_hall_SI": "regression_tests/baseline/BASE_uni_adiab_hall_SI_k2_0.5pi_k3_0.87.dat",
+    "uni_hall_elecinertia_SI": "regression_tests/baseline/BASE_uni_hall_elecinertia_SI_k2_5_k3_8.66.dat",
+    "uni_hall_elecinertia_SI2": "regression_tests/baseline/BASE_uni_hall_elecinertia_SI2_k2_5_k3_8.66.dat",
+    "taylor_couette_SI": "regression_tests/baseline/BASE_taylor_couette_SI_k2_0_k3_1.dat",
+    "uni_resistive_SI": "regression_tests/baseline/BASE_uni_resistive_SI_k2_0_k3_1.dat",
+    "couette_SI": "regression_tests/baseline/BASE_couette_SI_k2_0_k3_1.dat",
+    "couette_heating_SI": "regression_tests/baseline/BASE_couette_heating_SI_k2_0_k3_1.dat",
+    "rotating_cylinder_SI": "regression_tests/baseline/BASE_rotating_cylinder_SI_k2_1_k3_0.dat",
+    "rti_theta_pinch_hd_SI": "regression_tests/baseline/BASE_rti_theta_pinch_hd_SI_k2_1_k3_0.dat",
+    "rti_theta_pinch_mhd_SI": "regression_tests/baseline/BASE_rti_theta_pinch_mhd_SI_k2_1_k3_0.1.dat",
+    "hall_harris_sheet_QR": "regression_tests/baseline/BASE_hall_harris_sheet_QR_k2_0.155_k3_0.01.dat",
     "mri_matrix": "pylbo_tests/utility_files/v2.0.0_mri_matrix.dat",
     # the only stored run with eigenvectors, eigenfunctions AND residuals (rows N1 of the scope table)
     "mri_subset_efs": "pylbo_tests/utility_files/v2.0.0_mri_subset_efs.dat",
