@@ -342,41 +342,12 @@ __device__ __forceinline__ void publish_node(const StageArgs& a, size_t node, in
 
 // Unit upper triangular solve by one warp: lane i holds r_i and leaves with x_i.  U is packed by
 // columns with rows already divided by their diagonal entry; the diagonal slot holds 1 / U_ii.
-// Blocks of four columns: one round of shuffles brings the four right-hand sides of the block to
-// every lane, every lane solves the 4 x 4 unit triangle itself (its entries are broadcast reads)
-// and applies the four columns to its own row.  Per entry the subtractions happen in the same
-// order (descending column) as in a column-at-a-time substitution - bit-identical results - but
-// the dependent chain is one shuffle round + 4 complex FMAs per FOUR unknowns instead of one
-// shuffle round + one FMA per unknown (~1400 -> ~850 cycles for 32 unknowns).
+// One column per step: broadcast x_k (shuffle), one complex FMA per lane; the next columns are
+// prefetched four steps ahead.  Measured alone on the B200 (scripts/micro/trisolve.cu): 1540 cycles
+// per solve (48 per unknown = shuffle + two dependent DFMA).  Variants that broadcast four unknowns
+// per shuffle round and let every lane solve the 4 x 4 triangle itself were slower (1900 cycles
+// branch-free with the factor in registers, 3560 with a divergent update), not faster.
 __device__ __forceinline__ cd unit_upper_solve(const cd* U, cd r, int lane) {
-  r = r * U[tri_up_off(lane) + lane];
-#pragma unroll
-  for (int kb = SB / 4 - 1; kb >= 0; --kb) {
-    const int c0 = 4 * kb;
-    const cd* k1 = U + tri_up_off(c0 + 1);
-    const cd* k2 = U + tri_up_off(c0 + 2);
-    const cd* k3 = U + tri_up_off(c0 + 3);
-    const int li = min(lane, c0);   // rows above the block use their own entries of the four columns
-    const cd w0 = U[tri_up_off(c0) + li], w1 = k1[li], w2 = k2[li], w3 = k3[li];
-    const cd u01 = k1[c0], u02 = k2[c0], u12 = k2[c0 + 1], u03 = k3[c0], u13 = k3[c0 + 1], u23 = k3[c0 + 2];
-    const cd a0 = shfl_cd(r, c0), a1 = shfl_cd(r, c0 + 1), a2 = shfl_cd(r, c0 + 2), x3 = shfl_cd(r, c0 + 3);
-    cd x2 = a2; cfms(x2, u23, x3);
-    cd x1 = a1; cfms(x1, u13, x3); cfms(x1, u12, x2);
-    cd x0 = a0; cfms(x0, u03, x3); cfms(x0, u02, x2); cfms(x0, u01, x1);
-    if (lane < c0) {
-      cfms(r, w3, x3); cfms(r, w2, x2); cfms(r, w1, x1); cfms(r, w0, x0);
-    } else if (lane < c0 + 4) {
-      const int j = lane - c0;
-      r = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
-    }
-  }
-  return r;
-}
-
-// Column-at-a-time variant: 16 DFMA per four unknowns instead of 40.  The first-stage kernel runs up to
-// 24 of these substitutions per SM at once and is bound by FP64 issue, not by the chain of one warp
-// (measured: the blocked variant above made backward stage 0 slower, 39.5 -> 49.9 us at G = 10 001).
-__device__ __forceinline__ cd unit_upper_solve_seq(const cd* U, cd r, int lane) {
   r = r * U[tri_up_off(lane) + lane];
   cd u[4];
 #pragma unroll
@@ -439,7 +410,7 @@ __device__ __forceinline__ void chunk_backward(const StageArgs& a, const Ring& r
       }
       if (solver) {
         mbar_wait(&ur.full[mine.slot], mine.phase);
-        r = unit_upper_solve_seq(ur.slots + mine.slot * ur.stride, r, lane);
+        r = unit_upper_solve(ur.slots + mine.slot * ur.stride, r, lane);
         const int qm = 2 * (i0 + warp) * s + s;
         z[qm * SB + lane] = r;
         publish_node(a, unknown_index(a, r0 + qm), lane, r);
@@ -739,7 +710,6 @@ __global__ void __launch_bounds__(RING_THREADS) slu_fused_stage_kernel(const __g
 //   * a pair is worked on by four warps (thread = row r of an octet, column group q: 8 columns
 //     each, two shuffle rounds instead of a partial-sum exchange through shared memory), so the
 //     two pairs of a level run concurrently on the two halves of the CTA;
-//   * the U substitution is blocked by four columns (unit_upper_solve).
 // Hand-offs between CTAs are the same mailboxes as above.
 constexpr int UP_THREADS = 256;
 constexpr int UP_MAXPAIRS = 3;                              // mu <= 2: two pairs + one pair
@@ -752,7 +722,17 @@ struct UpperArgs {
   int nst;                       // stages of this launch; the last one is the top stage
   int cta0[MAX_FUSED + 1];       // first CTA of each stage
   StageArgs st[MAX_FUSED];
+  // Back-substitution records [E | F | U] of the first stage's upper levels: pf_count records from pf_first on.
+  // This launch is a dependency chain that leaves HBM idle; the CTAs of its first stage use the wait for their
+  // boundary unknowns to pull those records into L2 (cp.async.bulk.prefetch.L2), so that the backward first-stage
+  // kernel that follows streams only its lowest level from HBM.
+  const cd* pf_first;
+  int pf_count;
 };
+
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
+}
 
 __device__ __forceinline__ void group_sync(int grp) {
   asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
@@ -809,41 +789,60 @@ __device__ __forceinline__ void up_pair_backward_rhs(const cd* rec, const cd* zl
   if (q == 0) r[row] = g[row] - acc;
 }
 
-// 64 x 64 unit upper triangular solve by one warp (rows lane and lane + 32), column-major with
-// leading dimension 64, diagonal slot = 1 / U_ii; blocked by four columns like unit_upper_solve
-__device__ __forceinline__ void unit_upper_solve64(const cd* U, cd& y0, cd& y1, int lane) {
+// 64 x 64 unit upper triangular solve by one warp (rows lane and lane + 32), column-major with leading
+// dimension 64, diagonal slot = 1 / U_ii.  Four columns per shuffle round; branch-free (rows at or below a
+// block multiply zeros) with the next block's entries loaded before the current block's chain:
+// 3650 cycles against 8950 for the version with a divergent update (scripts/micro/trisolve.cu).
+struct TopBlk { cd p0, p1, p2, p3, q0, q1, q2, q3, u01, u02, u12, u03, u13, u23; };   // p: row lane, q: row lane + 32
+template <bool HI>
+__device__ __forceinline__ TopBlk top_load_blk(const cd* __restrict__ U, int c0, int lane) {
+  const cd* k0 = U + c0 * 64;
+  const cd z{0.0, 0.0};
+  TopBlk b;
+  const bool pa = lane < c0;
+  b.p0 = pa ? k0[lane] : z; b.p1 = pa ? k0[64 + lane] : z; b.p2 = pa ? k0[128 + lane] : z; b.p3 = pa ? k0[192 + lane] : z;
+  b.q0 = z; b.q1 = z; b.q2 = z; b.q3 = z;
+  if (HI) {
+    const bool qa = lane + 32 < c0;
+    const int i = min(lane + 32, c0);
+    b.q0 = qa ? k0[i] : z; b.q1 = qa ? k0[64 + i] : z; b.q2 = qa ? k0[128 + i] : z; b.q3 = qa ? k0[192 + i] : z;
+  }
+  b.u01 = k0[64 + c0]; b.u02 = k0[128 + c0]; b.u12 = k0[128 + c0 + 1];
+  b.u03 = k0[192 + c0]; b.u13 = k0[192 + c0 + 1]; b.u23 = k0[192 + c0 + 2];
+  return b;
+}
+template <bool HI>
+__device__ __forceinline__ void top_step_blk(const TopBlk& b, cd& y0, cd& y1, int c0, int lane) {
+  const cd src = HI ? y1 : y0;
+  const cd a0 = shfl_cd(src, c0 & 31), a1 = shfl_cd(src, (c0 + 1) & 31), a2 = shfl_cd(src, (c0 + 2) & 31),
+           x3 = shfl_cd(src, (c0 + 3) & 31);
+  cfms(y0, b.p3, x3); if (HI) cfms(y1, b.q3, x3);
+  cd x2 = a2; cfms(x2, b.u23, x3);
+  cfms(y0, b.p2, x2); if (HI) cfms(y1, b.q2, x2);
+  cd x1 = a1; cfms(x1, b.u13, x3); cfms(x1, b.u12, x2);
+  cfms(y0, b.p1, x1); if (HI) cfms(y1, b.q1, x1);
+  cd x0 = a0; cfms(x0, b.u03, x3); cfms(x0, b.u02, x2); cfms(x0, b.u01, x1);
+  cfms(y0, b.p0, x0); if (HI) cfms(y1, b.q0, x0);
+  const int j = lane - (c0 & 31);
+  cd& t = HI ? y1 : y0;
+  t = j == 0 ? x0 : t; t = j == 1 ? x1 : t; t = j == 2 ? x2 : t; t = j == 3 ? x3 : t;
+}
+__device__ __forceinline__ void unit_upper_solve64(const cd* __restrict__ U, cd& y0, cd& y1, int lane) {
   y0 = y0 * U[lane * 64 + lane];
   y1 = y1 * U[(lane + 32) * 64 + lane + 32];
-#pragma unroll 4
-  for (int kb = 15; kb >= 0; --kb) {
-    const int c0 = 4 * kb;
-    const bool hi = kb >= 8;
-    const cd* k0 = U + c0 * 64;
-    const cd* k1 = k0 + 64;
-    const cd* k2 = k0 + 128;
-    const cd* k3 = k0 + 192;
-    const cd u01 = k1[c0], u02 = k2[c0], u12 = k2[c0 + 1], u03 = k3[c0], u13 = k3[c0 + 1], u23 = k3[c0 + 2];
-    const cd src = hi ? y1 : y0;
-    const cd a0 = shfl_cd(src, c0 & 31), a1 = shfl_cd(src, (c0 + 1) & 31), a2 = shfl_cd(src, (c0 + 2) & 31),
-             x3 = shfl_cd(src, (c0 + 3) & 31);
-    cd x2 = a2; cfms(x2, u23, x3);
-    cd x1 = a1; cfms(x1, u13, x3); cfms(x1, u12, x2);
-    cd x0 = a0; cfms(x0, u03, x3); cfms(x0, u02, x2); cfms(x0, u01, x1);
-    if (hi || lane < c0) {
-      cfms(y0, k3[lane], x3); cfms(y0, k2[lane], x2); cfms(y0, k1[lane], x1); cfms(y0, k0[lane], x0);
-    } else if (lane < c0 + 4) {
-      const int j = lane - c0;
-      y0 = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
-    }
-    if (hi) {
-      const int i = lane + 32;
-      if (i < c0) {
-        cfms(y1, k3[i], x3); cfms(y1, k2[i], x2); cfms(y1, k1[i], x1); cfms(y1, k0[i], x0);
-      } else if (i < c0 + 4) {
-        const int j = i - c0;
-        y1 = j == 0 ? x0 : (j == 1 ? x1 : (j == 2 ? x2 : x3));
-      }
-    }
+  TopBlk cur = top_load_blk<true>(U, 60, lane);
+#pragma unroll
+  for (int kb = 15; kb >= 8; --kb) {
+    const TopBlk nxt = kb > 8 ? top_load_blk<true>(U, 4 * kb - 4, lane) : top_load_blk<false>(U, 4 * kb - 4, lane);
+    top_step_blk<true>(cur, y0, y1, 4 * kb, lane);
+    cur = nxt;
+  }
+#pragma unroll
+  for (int kb = 7; kb >= 0; --kb) {
+    TopBlk nxt = cur;
+    if (kb > 0) nxt = top_load_blk<false>(U, 4 * kb - 4, lane);
+    top_step_blk<false>(cur, y0, y1, 4 * kb, lane);
+    cur = nxt;
   }
 }
 
@@ -910,6 +909,12 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   pdl_launch_dependents();
   pdl_wait();   // everything below reads what earlier kernels wrote
   TRACE_MARK(1, 2);
+  // the top system's boundary right-hand sides do not depend on this launch: their load overlaps the wait for the rows
+  cd bvec{0.0, 0.0};
+  if (top && tid < 64 && (tid < 16 || tid >= 48)) {
+    if (tid < 16) bvec = ldcg_cd(a.b + tid);
+    else if (a.n_pad - 1 < a.n) bvec = ldcg_cd(a.b + static_cast<size_t>(a.n_pad - 1) * 16 + tid - 48);
+  }
   // ---- input rows
   if (tid < cnt * SB) {
     const cd* src = a.fin + static_cast<size_t>(r0) * SB + tid;
@@ -938,6 +943,12 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       if (a.fout_clear != nullptr) a.fout_clear[static_cast<size_t>(chunk) * SB + tid] = mbox_empty();
       a.fout[static_cast<size_t>(chunk) * SB + tid] = cur[tid];
     }
+    if (s == 0 && f.pf_count > 0 && tid == UP_THREADS - 1) {   // this CTA's share of the L2 prefetch (see UpperArgs)
+      const uint64_t keep = l2_policy_evict_last();
+      const int nc = f.cta0[1] - f.cta0[0];
+      for (int i = chunk; i < f.pf_count; i += nc)
+        l2_prefetch(f.pf_first + static_cast<size_t>(i) * PAIR_STRIDE + PR_E, sizeof(cd) * UP_BWD_ELEMS, keep);
+    }
     // boundary unknowns of the chunk
     if (tid < 2 * SB) {
       const bool right = tid >= SB;
@@ -947,13 +958,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   } else {
     // ---- dense top system [boundary row of node 0 ; last reduced row ; boundary row of node n_pad - 1]
     const cd* toprec = recs + PAIR_STRIDE;
-    if (tid < 64) {
-      cd v{0.0, 0.0};
-      if (tid < 16) v = a.b[tid];
-      else if (tid < 48) v = cur[tid - 16];
-      else if (a.n_pad - 1 < a.n) v = a.b[static_cast<size_t>(a.n_pad - 1) * 16 + tid - 48];
-      tvec[tid] = v;
-    }
+    if (tid < 64) tvec[tid] = (tid >= 16 && tid < 48) ? cur[tid - 16] : bvec;
     mbar_wait(&bars[2 * UP_MAXPAIRS], 0u);
     __syncthreads();
     {   // y = Linv (P t): thread = (row, 16 columns)
@@ -1716,6 +1721,24 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
         ctas += i == u.nst - 1 ? 1 : fst[i].nchunks;
       }
       u.cta0[u.nst] = ctas;
+      // L2 prefetch for the backward first-stage kernel: its upper levels, as many as fit the budget (the lowest
+      // level is half of all records and is left to stream from HBM while the prefetched levels are consumed).
+      // OFF by default (LGPU_SLU_L2PF_MB = 0): measured at G = 10 001 with 90 MB prefetched, the backward first-stage
+      // kernel gained 2.6 us but the mailbox round trips of this launch, queued behind the prefetch traffic, lost 6 us.
+      static const double pf_mb = [] { const char* e = std::getenv("LGPU_SLU_L2PF_MB"); return e ? atof(e) : 0.0; }();
+      if (sf == 1 && u.nst >= 2) {
+        const SluStage& s0 = plan.stages[0];
+        int lo = s0.mu;   // prefetch levels [lo, mu)
+        size_t recs = 0;
+        while (lo > 0 && (recs + plan.levels[lo - 1].npairs) * sizeof(cd) * UP_BWD_ELEMS <= pf_mb * 1.0e6) {
+          --lo;
+          recs += plan.levels[lo].npairs;
+        }
+        if (recs > 0) {
+          u.pf_first = d.pairs + plan.levels[lo].off_pairs * PAIR_STRIDE;
+          u.pf_count = static_cast<int>(recs);
+        }
+      }
       launch_pdl(slu_upper_kernel, dim3(ctas), dim3(UP_THREADS), UP_SMEM, stream, u);
     } else {
       FusedArgs f{};
