@@ -827,21 +827,23 @@ __device__ __forceinline__ void top_step_blk(const TopBlk& b, cd& y0, cd& y1, in
   cd& t = HI ? y1 : y0;
   t = j == 0 ? x0 : t; t = j == 1 ? x1 : t; t = j == 2 ? x2 : t; t = j == 3 ? x3 : t;
 }
+// Rolled loops on purpose: this code runs once per launch on one warp, and fully unrolled it is 64 KB of
+// straight-line instructions - with a cold instruction cache (first launch after the GPU was idle) fetching them
+// cost 33 us, measured with the kernel timeline (scripts/solve_trace.py).
 __device__ __forceinline__ void unit_upper_solve64(const cd* __restrict__ U, cd& y0, cd& y1, int lane) {
   y0 = y0 * U[lane * 64 + lane];
   y1 = y1 * U[(lane + 32) * 64 + lane + 32];
   TopBlk cur = top_load_blk<true>(U, 60, lane);
-#pragma unroll
-  for (int kb = 15; kb >= 8; --kb) {
-    const TopBlk nxt = kb > 8 ? top_load_blk<true>(U, 4 * kb - 4, lane) : top_load_blk<false>(U, 4 * kb - 4, lane);
-    top_step_blk<true>(cur, y0, y1, 4 * kb, lane);
+#pragma unroll 1
+  for (int c0 = 60; c0 >= 32; c0 -= 4) {
+    const TopBlk nxt = top_load_blk<true>(U, c0 - 4, lane);   // c0 - 4 = 28: rows lane + 32 lie below the block, q = 0
+    top_step_blk<true>(cur, y0, y1, c0, lane);
     cur = nxt;
   }
-#pragma unroll
-  for (int kb = 7; kb >= 0; --kb) {
-    TopBlk nxt = cur;
-    if (kb > 0) nxt = top_load_blk<false>(U, 4 * kb - 4, lane);
-    top_step_blk<false>(cur, y0, y1, 4 * kb, lane);
+#pragma unroll 1
+  for (int c0 = 28; c0 >= 0; c0 -= 4) {
+    const TopBlk nxt = top_load_blk<false>(U, max(c0 - 4, 0), lane);
+    top_step_blk<false>(cur, y0, y1, c0, lane);
     cur = nxt;
   }
 }
