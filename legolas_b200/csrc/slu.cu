@@ -98,6 +98,7 @@ __device__ __forceinline__ void trace_mark(int which, int slot) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_trace[which][blockIdx.x * TRACE_SLOTS + slot] = t;
   }
+  __syncwarp();   // thread 0 must rejoin its warp here: a warp left diverged takes the slow path of every shuffle
 }
 __device__ __forceinline__ void trace_value(int which, int slot, unsigned long long v) {
   if (threadIdx.x == 0 && blockIdx.x < TRACE_CTAS) g_trace[which][blockIdx.x * TRACE_SLOTS + slot] = v;
@@ -745,48 +746,77 @@ __device__ __forceinline__ cd quad_sum(cd v) {   // over the four column groups:
   return v;
 }
 
-// forward sweep of one pair by 128 threads: out = (P s)_2 - M2 (P s)_1, g = L11^-1 (P s)_1
-__device__ __forceinline__ void up_pair_forward(const cd* rec, const cd* s, cd* out, cd* g, int t) {
+// One pair is worked on by 128 threads: thread = (row r of an octet of rows, column group q = 8 columns q, q + 4, ...).
+// The factor records are static, so every thread copies its 16 + 16 matrix entries of the forward step (and later
+// of the back substitution) from shared memory into REGISTERS while it waits for its inputs; a pair step on the
+// critical path is then 8 broadcast reads of the right-hand side, 16 complex FMAs and two shuffle rounds, instead
+// of 24 - 32 KB streamed from shared memory per pair (measured with the kernel timeline: 0.75 us per forward level
+// and 0.32 us per right-hand side before).
+struct FwdRegs {
+  cd m[8], l[8];   // M2(row, c_k) and L11^-1(row, c_k) (zero above the diagonal), c_k = q + 4 k
+  int src[8];      // perm[c_k]: which entry of the stacked right-hand sides multiplies column c_k
+  int src2;        // perm[32 + row]
+};
+struct BwdRegs {
+  cd e[8], f[8];   // E(row, c_k), F(row, c_k)
+};
+__device__ __forceinline__ void load_fwd(const cd* rec, int t, FwdRegs& R) {
   const int lane = t & 31, q = lane >> 3, row = 8 * (t >> 5) + (lane & 7);
   const uint8_t* perm = reinterpret_cast<const uint8_t*>(rec + PR_PERM);
   const cd* L = rec + PR_L11I;
   const cd* M = rec + PR_L21;
-  cd v1[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) v1[k] = s[perm[q + 4 * k]];
-  cd ga{0.0, 0.0}, gb{0.0, 0.0}, oa{0.0, 0.0}, ob{0.0, 0.0};
-#pragma unroll
-  for (int k = 0; k < 8; k += 2) {
-    const int c = q + 4 * k, d = c + 4;
-    cfma(oa, M[c * SB + row], v1[k]);
-    cfma(ob, M[d * SB + row], v1[k + 1]);
-    if (c <= row) cfma(ga, L[tri_lo_off(c) + row - c], v1[k]);
-    if (d <= row) cfma(gb, L[tri_lo_off(d) + row - d], v1[k + 1]);
+  for (int k = 0; k < 8; ++k) {
+    const int c = q + 4 * k;
+    R.m[k] = M[c * SB + row];
+    R.l[k] = c <= row ? L[tri_lo_off(c) + row - c] : cd{0.0, 0.0};
+    R.src[k] = perm[c];
   }
-  const cd gs = quad_sum(ga + gb), os = quad_sum(oa + ob);
-  if (q == 0) {
-    out[row] = s[perm[SB + row]] - os;
-    g[row] = gs;
-  }
+  R.src2 = perm[SB + row];
 }
-
-// right-hand side of the back substitution of one pair by 128 threads: r = g - E z_left - F z_right
-__device__ __forceinline__ void up_pair_backward_rhs(const cd* rec, const cd* zl, const cd* zr, const cd* g,
-                                                     cd* r, int t) {
+__device__ __forceinline__ void load_bwd(const cd* rec, int t, BwdRegs& R) {
   const int lane = t & 31, q = lane >> 3, row = 8 * (t >> 5) + (lane & 7);
   const cd* E = rec + PR_E;
   const cd* F = rec + PR_F;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    R.e[k] = E[(q + 4 * k) * SB + row];
+    R.f[k] = F[(q + 4 * k) * SB + row];
+  }
+}
+// forward sweep of one pair: out = (P s)_2 - M2 (P s)_1 ; returns g = L11^-1 (P s)_1 of this thread's row (q == 0)
+__device__ __forceinline__ cd up_pair_forward(const FwdRegs& R, const cd* s, cd* out, int t) {
+  const int lane = t & 31, q = lane >> 3, row = 8 * (t >> 5) + (lane & 7);
+  cd v1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v1[k] = s[R.src[k]];
+  const cd s2 = s[R.src2];
+  cd ga{0.0, 0.0}, gb{0.0, 0.0}, oa{0.0, 0.0}, ob{0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    cfma(oa, R.m[k], v1[k]);
+    cfma(ob, R.m[k + 1], v1[k + 1]);
+    cfma(ga, R.l[k], v1[k]);
+    cfma(gb, R.l[k + 1], v1[k + 1]);
+  }
+  const cd gs = quad_sum(ga + gb), os = quad_sum(oa + ob);
+  if (q == 0) out[row] = s2 - os;
+  return gs;
+}
+// right-hand side of the back substitution of one pair: r = g - E z_left - F z_right
+__device__ __forceinline__ void up_pair_backward_rhs(const BwdRegs& R, const cd* zl, const cd* zr, cd g, cd* r, int t) {
+  const int lane = t & 31, q = lane >> 3, row = 8 * (t >> 5) + (lane & 7);
   cd ea{0.0, 0.0}, eb{0.0, 0.0}, fa{0.0, 0.0}, fb{0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
     const int c = q + 4 * k, d = c + 4;
-    cfma(ea, E[c * SB + row], zl[c]);
-    cfma(eb, E[d * SB + row], zl[d]);
-    cfma(fa, F[c * SB + row], zr[c]);
-    cfma(fb, F[d * SB + row], zr[d]);
+    cfma(ea, R.e[k], zl[c]);
+    cfma(eb, R.e[k + 1], zl[d]);
+    cfma(fa, R.f[k], zr[c]);
+    cfma(fb, R.f[k + 1], zr[d]);
   }
   const cd acc = quad_sum((ea + eb) + (fa + fb));
-  if (q == 0) r[row] = g[row] - acc;
+  if (q == 0) r[row] = g - acc;
 }
 
 // 64 x 64 unit upper triangular solve by one warp (rows lane and lane + 32), column-major with leading
@@ -848,9 +878,9 @@ __device__ __forceinline__ void unit_upper_solve64(const cd* __restrict__ U, cd&
   }
 }
 
-// smem: [3 pair records | (top CTA) 1 pair record + dense top record][level rows 2 x 4 x 32][g 3 x 32]
+// smem: [3 pair records | (top CTA) 1 pair record + dense top record][level rows 2 x 4 x 32]
 //       [z 5 x 32][r 2 x 32][t 64][partial sums 4 x 64][7 barriers]
-constexpr size_t UP_SMEM = sizeof(cd) * (UP_REC_ELEMS + 2 * 4 * SB + UP_MAXPAIRS * SB + 5 * SB + 2 * SB + 64 + 4 * 64) +
+constexpr size_t UP_SMEM = sizeof(cd) * (UP_REC_ELEMS + 2 * 4 * SB + 5 * SB + 2 * SB + 64 + 4 * 64) +
                            sizeof(uint64_t) * (2 * UP_MAXPAIRS + 2);
 
 __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_constant__ UpperArgs f) {
@@ -858,13 +888,13 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   SmemCursor sc{smem_raw};
   cd* recs = sc.take<cd>(UP_REC_ELEMS);
   cd* rows = sc.take<cd>(2 * 4 * SB);
-  cd* gbuf = sc.take<cd>(UP_MAXPAIRS * SB);
   cd* z = sc.take<cd>(5 * SB);
   cd* rbuf = sc.take<cd>(2 * SB);
   cd* tvec = sc.take<cd>(64);
   cd* part = sc.take<cd>(4 * 64);
   uint64_t* bars = sc.take<uint64_t>(2 * UP_MAXPAIRS + 2);   // [2p] forward part of pair p, [2p + 1] backward part, [6] top record
   const int tid = threadIdx.x, lane = tid & 31, b = blockIdx.x;
+  const int grp = tid >> 7, t = tid & 127;
   TRACE_MARK(1, 0);
   int s = 0;
   while (s + 1 < f.nst && b >= f.cta0[s + 1]) ++s;
@@ -872,43 +902,68 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   const StageArgs& a = f.st[s];
   const bool top = s == f.nst - 1;
   const int chunk = b - f.cta0[s];
-  const int r0 = top ? 0 : chunk << a.mu;
-  const int cnt = top ? a.m0 : min(1 << a.mu, a.m0 - r0);
-  // pairs of the chunk, level by level: slot0[lam] = first record slot of level lam
-  int slot0[3] = {0, 0, 0}, npair[2] = {0, 0};
-  for (int lam = 0; lam < a.mu; ++lam) {
-    npair[lam] = ((cnt + (1 << lam) - 1) >> lam) / 2;
-    slot0[lam + 1] = slot0[lam] + npair[lam];
-  }
+  const int mu = a.mu;
+  const int r0 = top ? 0 : chunk << mu;
+  const int cnt = top ? a.m0 : min(1 << mu, a.m0 - r0);
+  // pairs of the chunk: np0 <= 2 at its first level (record slots 0, 1), np1 <= 1 at its second (slot np0)
+  const int np0 = mu >= 1 ? cnt / 2 : 0;
+  const int m1 = (cnt + 1) >> 1;
+  const int np1 = mu >= 2 ? m1 / 2 : 0;
   // ---- prologue: every record this CTA will ever use -> shared memory (static data: no dependence on
-  // the kernels before this one)
+  // the kernels before this one), in order of use
   if (tid == 0) {
     for (int i = 0; i < 2 * UP_MAXPAIRS + 1; ++i) mbar_init(&bars[i], 1);
     ring_init_fence();
     const uint64_t keep = l2_policy_evict_last();
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int step = 0; step < a.mu; ++step) {
-        const int lam = pass == 0 ? step : a.mu - 1 - step;   // order of use
-        const size_t pair0 = a.lv[lam].off_pairs + (static_cast<size_t>(r0 >> lam) >> 1);
-        for (int i = 0; i < npair[lam]; ++i) {
-          const int p = slot0[lam] + i;
-          const cd* rec = a.pairs + (pair0 + i) * PAIR_STRIDE;
-          const int off = pass == 0 ? PR_PERM : PR_E;
-          const uint32_t bytes = static_cast<uint32_t>(sizeof(cd) * (pass == 0 ? UP_FWD_ELEMS : UP_BWD_ELEMS));
-          mbar_expect_tx(&bars[2 * p + pass], bytes);
-          bulk_g2s_hint(recs + p * PAIR_STRIDE + off, rec + off, bytes, &bars[2 * p + pass], keep);
-        }
-      }
-      if (pass == 0 && top) {
-        const uint32_t bytes = static_cast<uint32_t>(sizeof(cd) * TOP_STRIDE);
-        mbar_expect_tx(&bars[2 * UP_MAXPAIRS], bytes);
-        bulk_g2s_hint(recs + PAIR_STRIDE, a.top, bytes, &bars[2 * UP_MAXPAIRS], keep);
-      }
+    const cd* rec0 = a.pairs + (a.lv[0].off_pairs + (static_cast<size_t>(r0) >> 1)) * PAIR_STRIDE;
+    const cd* rec1 = mu >= 2 ? a.pairs + (a.lv[1].off_pairs + (static_cast<size_t>(r0 >> 1) >> 1)) * PAIR_STRIDE : nullptr;
+    constexpr uint32_t fwd_bytes = sizeof(cd) * UP_FWD_ELEMS, bwd_bytes = sizeof(cd) * UP_BWD_ELEMS;
+    for (int i = 0; i < np0; ++i) {
+      mbar_expect_tx(&bars[2 * i], fwd_bytes);
+      bulk_g2s_hint(recs + i * PAIR_STRIDE + PR_PERM, rec0 + i * PAIR_STRIDE + PR_PERM, fwd_bytes, &bars[2 * i], keep);
+    }
+    if (np1) {
+      mbar_expect_tx(&bars[2 * np0], fwd_bytes);
+      bulk_g2s_hint(recs + np0 * PAIR_STRIDE + PR_PERM, rec1 + PR_PERM, fwd_bytes, &bars[2 * np0], keep);
+    }
+    if (top) {
+      constexpr uint32_t bytes = sizeof(cd) * TOP_STRIDE;
+      mbar_expect_tx(&bars[2 * UP_MAXPAIRS], bytes);
+      bulk_g2s_hint(recs + PAIR_STRIDE, a.top, bytes, &bars[2 * UP_MAXPAIRS], keep);
+    }
+    if (np1) {
+      mbar_expect_tx(&bars[2 * np0 + 1], bwd_bytes);
+      bulk_g2s_hint(recs + np0 * PAIR_STRIDE + PR_E, rec1 + PR_E, bwd_bytes, &bars[2 * np0 + 1], keep);
+    }
+    for (int i = 0; i < np0; ++i) {
+      mbar_expect_tx(&bars[2 * i + 1], bwd_bytes);
+      bulk_g2s_hint(recs + i * PAIR_STRIDE + PR_E, rec0 + i * PAIR_STRIDE + PR_E, bwd_bytes, &bars[2 * i + 1], keep);
     }
   }
   __syncthreads();
   TRACE_MARK(1, 1);
   pdl_launch_dependents();
+  // ---- this thread's share of the forward matrices -> registers.  Group g owns pair g of the first level (A);
+  // group 0 also owns the pair of the second level (B).
+  const bool hasA = grp < np0, hasB = grp == 0 && np1 > 0;
+  FwdRegs FA, FB;
+  BwdRegs BA, BB;
+  if (hasA) { mbar_wait(&bars[2 * grp], 0u); load_fwd(recs + grp * PAIR_STRIDE, t, FA); }
+  if (hasB) { mbar_wait(&bars[2 * np0], 0u); load_fwd(recs + np0 * PAIR_STRIDE, t, FB); }
+  // dense top system: thread = (row, 16 columns) of Linv; the top CTA has no second-level pair, so the entries
+  // live in the registers of FB (m: columns 0 .. 7 of the thread's 16, l: 8 .. 15, src[0 .. 3]: permutation bytes)
+  const cd* toprec = recs + PAIR_STRIDE;
+  if (top) {
+    mbar_wait(&bars[2 * UP_MAXPAIRS], 0u);
+    const int row = tid & 63, cg = tid >> 6;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      FB.m[c] = toprec[TOP_LINV + (cg * 16 + c) * 64 + row];
+      FB.l[c] = toprec[TOP_LINV + (cg * 16 + 8 + c) * 64 + row];
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) FB.src[w] = static_cast<int>(reinterpret_cast<const uint32_t*>(toprec)[cg * 4 + w]);
+  }
   pdl_wait();   // everything below reads what earlier kernels wrote
   TRACE_MARK(1, 2);
   // the top system's boundary right-hand sides do not depend on this launch: their load overlaps the wait for the rows
@@ -924,18 +979,19 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   }
   __syncthreads();
   TRACE_MARK(1, 3);
-  const int grp = tid >> 7, t = tid & 127;
   cd* cur = rows;
   cd* nxt = rows + 4 * SB;
-  // ---- forward: the pairs of a level side by side
-  for (int lam = 0; lam < a.mu; ++lam) {
-    const int ml = (cnt + (1 << lam) - 1) >> lam, np = npair[lam];
-    if (grp < np) {
-      const int p = slot0[lam] + grp;
-      mbar_wait(&bars[2 * p], 0u);
-      up_pair_forward(recs + p * PAIR_STRIDE, cur + 2 * grp * SB, nxt + grp * SB, gbuf + p * SB, t);
-    }
-    if ((ml & 1) && tid >= UP_THREADS - 32) nxt[np * SB + lane] = cur[2 * np * SB + lane];   // odd row: carried up
+  // ---- forward: the pairs of a level side by side; g of a pair stays in the registers of its q == 0 threads
+  cd gA{0.0, 0.0}, gB{0.0, 0.0};
+  if (mu >= 1) {
+    if (hasA) gA = up_pair_forward(FA, cur + 2 * grp * SB, nxt + grp * SB, t);
+    if ((cnt & 1) && tid >= UP_THREADS - 32) nxt[np0 * SB + lane] = cur[2 * np0 * SB + lane];   // odd row: carried up
+    __syncthreads();
+    cd* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (mu >= 2) {
+    if (hasB) gB = up_pair_forward(FB, cur, nxt, t);
+    if ((m1 & 1) && tid >= UP_THREADS - 32) nxt[np1 * SB + lane] = cur[2 * np1 * SB + lane];
     __syncthreads();
     cd* tmp = cur; cur = nxt; nxt = tmp;
   }
@@ -951,6 +1007,9 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       for (int i = chunk; i < f.pf_count; i += nc)
         l2_prefetch(f.pf_first + static_cast<size_t>(i) * PAIR_STRIDE + PR_E, sizeof(cd) * UP_BWD_ELEMS, keep);
     }
+    // the matrices of the back substitution take the place of the forward ones while the unknowns are on their way
+    if (hasA) { mbar_wait(&bars[2 * grp + 1], 0u); load_bwd(recs + grp * PAIR_STRIDE, t, BA); }
+    if (hasB) { mbar_wait(&bars[2 * np0 + 1], 0u); load_bwd(recs + np0 * PAIR_STRIDE, t, BB); }
     // boundary unknowns of the chunk
     if (tid < 2 * SB) {
       const bool right = tid >= SB;
@@ -959,22 +1018,20 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
     }
   } else {
     // ---- dense top system [boundary row of node 0 ; last reduced row ; boundary row of node n_pad - 1]
-    const cd* toprec = recs + PAIR_STRIDE;
     if (tid < 64) tvec[tid] = (tid >= 16 && tid < 48) ? cur[tid - 16] : bvec;
-    mbar_wait(&bars[2 * UP_MAXPAIRS], 0u);
     __syncthreads();
-    {   // y = Linv (P t): thread = (row, 16 columns)
-      const uint8_t* perm = reinterpret_cast<const uint8_t*>(toprec);
-      const cd* Linv = toprec + TOP_LINV;
+    {   // y = Linv (P t)
       const int row = tid & 63, cg = tid >> 6;
       cd p0{0.0, 0.0}, p1{0.0, 0.0};
 #pragma unroll
       for (int c = 0; c < 16; c += 2) {
-        cfma(p0, Linv[(cg * 16 + c) * 64 + row], tvec[perm[cg * 16 + c]]);
-        cfma(p1, Linv[(cg * 16 + c + 1) * 64 + row], tvec[perm[cg * 16 + c + 1]]);
+        const uint32_t w = static_cast<uint32_t>(FB.src[c >> 2]);
+        cfma(p0, c < 8 ? FB.m[c] : FB.l[c - 8], tvec[(w >> (8 * (c & 3))) & 0xffu]);
+        cfma(p1, c < 8 ? FB.m[c + 1] : FB.l[c - 7], tvec[(w >> (8 * ((c + 1) & 3))) & 0xffu]);
       }
       part[cg * 64 + row] = p0 + p1;
     }
+    if (hasA) { mbar_wait(&bars[2 * grp + 1], 0u); load_bwd(recs + grp * PAIR_STRIDE, t, BA); }
     __syncthreads();
     TRACE_MARK(1, 13);
     if (tid < 32) {
@@ -985,33 +1042,40 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       publish_node(a, 0, lane, y0);
       z[cnt * SB + lane] = y1;
       publish_node(a, static_cast<size_t>(a.K - 1), lane, y1);
-      TRACE_MARK(1, 14);
     }
+    TRACE_MARK(1, 14);
   }
   __syncthreads();
   TRACE_MARK(1, 5);
   // ---- backward: z = U^-1 (g - E z_left - F z_right), upper level first, pairs of a level side by side
-  for (int lam = a.mu - 1; lam >= 0; --lam) {
-    const int st = 1 << lam, np = npair[lam];
-    if (grp < np) {
-      const int p = slot0[lam] + grp;
-      const cd* rec = recs + p * PAIR_STRIDE;
-      const int ql = 2 * grp * st, qr = min(ql + 2 * st, cnt), qm = ql + st;
-      mbar_wait(&bars[2 * p + 1], 0u);
-      if (lam == a.mu - 1) TRACE_MARK(1, 10);
-      up_pair_backward_rhs(rec, z + ql * SB, z + qr * SB, gbuf + p * SB, rbuf + grp * SB, t);
-      group_sync(grp);
-      if (lam == a.mu - 1) TRACE_MARK(1, 11);
-      if (t < 32) {
-        const cd x = unit_upper_solve(rec + PR_U, rbuf[grp * SB + lane], lane);
-        z[qm * SB + lane] = x;
-        publish_node(a, unknown_index(a, r0 + qm), lane, x);
-      }
-      if (lam == a.mu - 1) TRACE_MARK(1, 12);
+  if (hasB) {   // second level: one pair, rows 0 .. 3 of the chunk
+    const int qr = min(4, cnt);
+    TRACE_MARK(1, 10);
+    up_pair_backward_rhs(BB, z, z + qr * SB, gB, rbuf, t);
+    group_sync(0);
+    TRACE_MARK(1, 11);
+    if (t < 32) {
+      const cd x = unit_upper_solve(recs + np0 * PAIR_STRIDE + PR_U, rbuf[lane], lane);
+      z[2 * SB + lane] = x;
+      publish_node(a, unknown_index(a, r0 + 2), lane, x);
     }
-    __syncthreads();
-    TRACE_MARK(1, 6 + (a.mu - 1 - lam));
+    TRACE_MARK(1, 12);
   }
+  if (mu >= 2) {
+    __syncthreads();
+    TRACE_MARK(1, 6);
+  }
+  if (hasA) {
+    const int ql = 2 * grp, qr = min(ql + 2, cnt), qm = ql + 1;
+    up_pair_backward_rhs(BA, z + ql * SB, z + qr * SB, gA, rbuf + grp * SB, t);
+    group_sync(grp);
+    if (t < 32) {
+      const cd x = unit_upper_solve(recs + grp * PAIR_STRIDE + PR_U, rbuf[grp * SB + lane], lane);
+      z[qm * SB + lane] = x;
+      publish_node(a, unknown_index(a, r0 + qm), lane, x);
+    }
+  }
+  TRACE_MARK(1, 7);
 }
 
 // Single CTA: the top stage alone (problems too small for more than one stage above the first).
