@@ -373,6 +373,10 @@ def run_gpu(args):
     else:
         gathered = [per_rank]
 
+    sharded = None
+    if not args.no_sharded:
+        sharded = run_sharded_sections(args, rank, world, local_rank, device)
+
     if rank == 0:
         peak, peak_src = load_peaks()
         # dominant kernel class of the timed region (CUDA events around every launch)
@@ -391,7 +395,7 @@ def run_gpu(args):
                         for k, v in solver_kinds.items()}
         op_kinds = ("matvec", "fwd_stage0", "fwd_stage", "top_stage", "bwd_stage", "bwd_stage0")
         op_ms = sum(prof[k][0] for k in op_kinds)
-        n_op_total = prof["matvec"][1]
+        n_op_total = prof["fwd_stage0"][1]   # one first-stage launch per operator application (B x may be fused into it)
         op_gbs = 37120.0 * GRIDPTS * n_op_total / (op_ms * 1e-3) / 1e9 if op_ms > 0 else None
         # whole step on SURVEY section 8(d) bytes: assembly + factorisation + n_op operator applications +
         # one two-pass orthogonalisation per Arnoldi step + restarts + extraction, as logged per launch
@@ -427,7 +431,7 @@ def run_gpu(args):
                               "frac": round(step_gbs / peak, 4),
                               "ms_in_kernels_per_step": round(kernel_ms, 3),
                               "ms_outside_kernels_per_step": round(1e3 * sec_per_step - kernel_ms, 3)},
-            "op_roofline": {"what": "whole OP*x = (A - sigma B)^-1 B x (4 launches: B x, forward stage 0, fused upper stages + top system, backward stage 0), 37120*G algorithmic bytes",
+            "op_roofline": {"what": "whole OP*x = (A - sigma B)^-1 B x (3 launches: forward stage 0 with the B x product fused in, upper stages + top system, backward stage 0), 37120*G algorithmic bytes",
                             "achieved": round(op_gbs, 1) if op_gbs else None, "unit": "GB/s",
                             "frac": round(op_gbs / peak, 4) if op_gbs else None,
                             "us_per_op": round(1e3 * op_ms / max(n_op_total, 1), 2)},
@@ -436,6 +440,8 @@ def run_gpu(args):
             "phases_ms": ctx.phase_times(),
             "ranks": gathered,
         }
+        if sharded:
+            line.update(sharded)
         if world == 1 and not args.no_cpu_baseline:
             line["next_rows"] = time_next_rows(lb, heq, ctx, s, grid, fields, sigma)
         if cpu is not None:
@@ -449,6 +455,101 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- sharded workloads
+def run_sharded_sections(args, rank, world, local_rank, device):
+    """The two sharded workloads of BASELINE.json at this N, outside the headline's timed region:
+      scan  - config 4: the 32-shift scan of legolas_b200.workloads.SCAN_SHIFTS (unequal units, nev 20 / 10), handed out
+              longest first from a shared queue; after the timed pass rank 0 solves all 32 itself and compares
+      sweep - config 5: the 256-point (k2, k3) sweep at G = 2001, three units in flight per GPU
+    One untimed pass first (allocations, measured unit costs), then one timed pass between barriers; time = CUDA events
+    on an otherwise empty stream of each rank, max over ranks; the eigenvalue tables are gathered after the timed pass."""
+    import torch
+    import torch.distributed as dist
+
+    from legolas_b200 import sweep, workloads as wl
+
+    timer = torch.cuda.Stream(device=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed_pass(units, order, solvers, nev):
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(timer)
+        table, mine = sweep.run_queue(units, None, nev, order=order, solvers=solvers, gather=False)
+        torch.cuda.synchronize()
+        stop.record(timer)
+        barrier()
+        t = torch.tensor([start.elapsed_time(stop) / 1e3], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), sweep.merge_tables(table), mine
+
+    def total(values):
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    out = {}
+    # ---- config 4: multi-shift scan
+    units = list(wl.SCAN_SHIFTS)
+    order = wl.longest_first([u[2] for u in units])
+    solvers = [wl.ScanSolver(device=local_rank)]
+    timed_pass(units, order, solvers, wl.SCAN_NEV_MAX)
+    solvers[0].n_op = solvers[0].nconv_short = 0
+    sec, table, mine = timed_pass(units, order, solvers, wl.SCAN_NEV_MAX)
+    n_op, short = total([solvers[0].n_op, solvers[0].nconv_short])
+    counts = [None] * world
+    if world > 1:
+        dist.all_gather_object(counts, len(mine))
+    else:
+        counts = [len(mine)]
+    check = None
+    if rank == 0:   # union of the modes against a single-GPU run of the same units (bit-identical kernels)
+        ref = np.stack([solvers[0](u) for u in units])
+        same = np.array_equal(np.isnan(ref), np.isnan(table))
+        diff = float(np.nanmax(np.abs(np.nan_to_num(ref) - np.nan_to_num(table))))
+        modes = ref[~np.isnan(ref)]
+        distinct = len(np.unique(np.round(modes / 1e-7).astype(np.complex128)))
+        check = {"same_converged_sets": bool(same), "max_abs_diff_vs_single_gpu": diff,
+                 "modes_returned": int(modes.size), "distinct_modes": int(distinct)}
+    solvers[0].close()
+    out["scan"] = {"workload": f"config 4: {len(units)}-shift scan of the thermal branch at G={wl.SCAN_GRIDPTS} (nev 20 at 22 shifts, "
+                               "10 at 10), one factorisation + Arnoldi run per unit",
+                   "units": len(units), "seconds": sec, "units_per_s": len(units) / sec, "n_op_total": int(n_op),
+                   "units_short_of_nev": int(short), "units_per_rank": counts,
+                   "scheduling": "shared queue (torch.distributed store counter), longest first by operator-application estimate",
+                   "check": check}
+    # ---- config 5: wavenumber sweep
+    units = wl.sweep_units(args.sweep_units)
+    workers = max(1, args.sweep_workers)
+    solvers = [wl.SweepSolver(device=local_rank) for _ in range(workers)]
+    _, cost_table, _ = timed_pass(units, list(range(len(units))), solvers, wl.SWEEP_NEV)
+    # measured cost of every unit (operator applications of the untimed pass), gathered like the eigenvalues
+    costs = np.full((len(units), 1), np.nan + 0j)
+    for i, u in enumerate(units):
+        if u["cost"]:
+            costs[i, 0] = u["cost"]
+    costs = sweep.merge_tables(costs).real[:, 0]
+    for sv in solvers:
+        sv.n_op = sv.converged = 0
+    sec, table, mine = timed_pass(units, wl.longest_first(costs), solvers, wl.SWEEP_NEV)
+    n_op, conv = total([sum(sv.n_op for sv in solvers), sum(sv.converged for sv in solvers)])
+    for sv in solvers:
+        sv.close()
+    out["sweep"] = {"workload": f"config 5: kelvin_helmholtz_cd G={wl.SWEEP_GRIDPTS}, {len(units)}-point (k2,k3) sweep, per-unit shift from "
+                                f"a coarse QR-invert pre-scan, nev={wl.SWEEP_NEV} ncv={wl.SWEEP_NCV} maxiter={wl.SWEEP_MAXITER}",
+                    "units": len(units), "seconds": sec, "units_per_s": len(units) / sec, "n_op_total": int(n_op),
+                    "units_converged": int(conv), "units_in_flight_per_gpu": workers,
+                    "scheduling": "shared queue, longest first by the operator applications of the untimed pass",
+                    "max_growth_rate": float(np.nanmax(table.imag))}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -456,6 +557,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the scan (config 4) and sweep (config 5) sections")
+    ap.add_argument("--sweep-units", type=int, default=0, help="units of the config-5 sweep (0: all 256)")
+    ap.add_argument("--sweep-workers", type=int, default=3, help="units in flight per GPU in the config-5 sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

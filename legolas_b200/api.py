@@ -541,11 +541,13 @@ def build_matrices(settings: Settings, grid: np.ndarray, gauss_grid: np.ndarray,
     return Matrices(ctx=ctx, settings=settings)
 
 
-def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
+def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False, want_vectors: bool = True):
     """``call solve_evp(matrix_A, matrix_B, settings, omega, right_eigenvectors)`` for
     ``solver = "arnoldi"``, ``arpack_mode = "shift-invert"`` or ``"general"``.  Returns (omega, vr, arpack_cfg, stats);
     omega(nconv:) is NaN when ARPACK-style convergence was not reached for all nev (a warning,
-    not an error, in the reference: mod_arpack_type.f08:375-381)."""
+    not an error, in the reference: mod_arpack_type.f08:375-381).  ``want_vectors = False`` is the reference's
+    ``settings%io%should_compute_eigenvectors() == .false.`` (src/main.f08:124-153: ``right_eigenvectors`` is then a
+    dummy of size (2, 2) and zneupd is asked for eigenvalues only): vr is returned as None."""
     sv = settings.solvers
     if sv.solver == "inverse-iteration":
         # mod_solvers.f08:92-123 dispatch; one eigenpair, omega(1) / vr(:, 1)
@@ -575,7 +577,8 @@ def solve_evp(matrices: Matrices, settings: Settings, vr_view: bool = False):
     if math.isnan(sv.sigma.real) or math.isnan(sv.sigma.imag):
         raise LegolasError("sigma is not set")
     cfg = new_arpack_config(matrices.ctx.dim, mode=2, bmat="I", solver_settings=sv)
-    omega, vr, stats = matrices.ctx.shift_invert(cfg, complex(sv.sigma), sv.refine_steps, vr_view=vr_view)
+    omega, vr, stats = matrices.ctx.shift_invert(cfg, complex(sv.sigma), sv.refine_steps, vr_view=vr_view,
+                                                 want_vectors=want_vectors)
     cfg.info = stats["info"]
     cfg.iparam.update({5: stats["nconv"], 9: stats["n_op"], 10: stats["n_bx"], 11: stats["n_reorth"]})
     _parse_arnoldi_status(stats, cfg)

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -72,6 +74,7 @@ struct lgpu_ctx {
   int log_level = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  int demand_G = -1, demand = 0;   // slu_coresident_demand of the plan for G grid points (SolveTicket)
   std::string err;
 
   // matrices
@@ -141,11 +144,55 @@ struct lgpu_ctx {
 
 namespace {
 
+// Admission of concurrent calls from several contexts of one process on one device (one host thread per context,
+// e.g. a wavenumber sweep that keeps several small units in flight per GPU): a call runs while the SMs its solves may
+// hold waiting (slu_coresident_demand) fit the device next to those of the calls already running; a call whose
+// demand alone exceeds the device runs alone.  Every entry point synchronises its stream before it returns, so the
+// ticket covers all the launches of the call.
+struct SolveAdmission {
+  std::mutex m;
+  std::condition_variable cv;
+  int in_use[64] = {};
+  static SolveAdmission& get() { static SolveAdmission a; return a; }
+};
+class SolveTicket {
+ public:
+  SolveTicket(int dev, int demand) : dev_(dev >= 0 && dev < 64 ? dev : 0), demand_(demand) {
+    if (demand_ <= 0) return;
+    SolveAdmission& a = SolveAdmission::get();
+    const int budget = device_sm_count();
+    std::unique_lock<std::mutex> lk(a.m);
+    a.cv.wait(lk, [&] { return a.in_use[dev_] == 0 || a.in_use[dev_] + demand_ <= budget; });
+    a.in_use[dev_] += demand_;
+  }
+  ~SolveTicket() {
+    if (demand_ <= 0) return;
+    SolveAdmission& a = SolveAdmission::get();
+    { std::lock_guard<std::mutex> lk(a.m); a.in_use[dev_] -= demand_; }
+    a.cv.notify_all();
+  }
+  SolveTicket(const SolveTicket&) = delete;
+  SolveTicket& operator=(const SolveTicket&) = delete;
+ private:
+  int dev_, demand_;
+};
+
+int solve_demand(lgpu_ctx* c) {
+  if (c->G <= 0) return 0;
+  if (c->demand_G != c->G) {
+    c->demand = slu_coresident_demand(make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 2),
+                                                    env_int("LGPU_SLU_TOP", 2)));
+    c->demand_G = c->G;
+  }
+  return c->demand;
+}
+
 template <typename F>
 int guarded(lgpu_ctx* ctx, F&& body) {
   if (!ctx) return LGPU_EINVAL;
   try {
     CUDA_CHECK(cudaSetDevice(ctx->device));
+    SolveTicket ticket(ctx->device, solve_demand(ctx));
     return body();
   } catch (const CudaError& e) {
     ctx->err = e.what();
@@ -437,6 +484,16 @@ void dev_apply_op_general(lgpu_ctx* c, const cd* x, cd* y, int refine) {
 void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
   if (c->factor_of_B) return dev_apply_op_general(c, x, y, refine);
   static const bool use_ell = [] { const char* e = std::getenv("LGPU_B_ELL"); return !(e && e[0] == '0'); }();
+  static const bool fuse_bx = [] { const char* e = std::getenv("LGPU_BX_FUSE"); return !(e && e[0] == '0'); }();
+  // B real with short rows (everything but Hall): the solve kernels form B x themselves, no product launch
+  if (use_ell && fuse_bx && refine == 0 && c->bell_real && c->bell_w >= 0 && c->bell_w <= 8 && x != y &&
+      c->splan.stages.size() >= 2) {
+    RhsEll ell;
+    ell.val = c->bell_rval.p; ell.col = c->bell_col.p; ell.x = x; ell.rows = c->G * BLK; ell.width = c->bell_w;
+    c->log.fused_bx += 1;
+    slu_solve(c->splan, c->sdev(), nullptr, y, c->stream, &c->log, &ell);
+    return;
+  }
   if (use_ell && c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
     bell_matvec(c->G, BEll{c->bell_val.p, c->bell_col.p, c->bell_width.p, c->bell_rval.p}, c->bell_w, c->bell_real, x, c->vu.p, c->stream,
                 &c->log);

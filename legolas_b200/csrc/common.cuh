@@ -167,6 +167,7 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
 
 struct LaunchLog {
   int64_t launches = 0;
+  int64_t fused_bx = 0;            // operator applications whose B x product ran inside the solve kernels
   bool profiling = false;
   cudaStream_t stream = nullptr;
   std::vector<cudaEvent_t> pool;   // start/stop pairs

@@ -136,7 +136,66 @@ struct StageArgs {
   cd* zbox;          // this solve's copy of the solved super nodes (K x 32), written next to xv
   cd* zbox_clear;    // the other parity's copy
   int poll_z;        // boundary unknowns of a chunk come from zbox (polled) instead of xv
+  RhsEll ell;        // ell.x != nullptr: the right-hand side is B v, formed on the fly (b is not read)
+  int fin_is_rhs;    // first stage: fin points into the right-hand side itself
 };
+
+// entry idx of the right-hand side
+__device__ __forceinline__ cd rhs_entry(const StageArgs& a, size_t idx) {
+  if (a.ell.x == nullptr) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(a.b + idx));
+    return cd{v.x, v.y};
+  }
+  double v[8];
+  int c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool on = k < a.ell.width;
+    v[k] = on ? __ldg(a.ell.val + static_cast<size_t>(k) * a.ell.rows + idx) : 0.0;
+    c[k] = on ? __ldg(a.ell.col + static_cast<size_t>(k) * a.ell.rows + idx) : 0;
+  }
+  cd acc{0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < a.ell.width) {
+      const double2 t = __ldg(reinterpret_cast<const double2*>(a.ell.x + c[k]));
+      acc.x = fma(v[k], t.x, acc.x);
+      acc.y = fma(v[k], t.y, acc.y);
+    }
+  }
+  return acc;
+}
+
+// two entries at once: all loads of a phase issued before any is used
+__device__ __forceinline__ void rhs_entry2(const StageArgs& a, size_t i0, size_t i1, cd& r0, cd& r1) {
+  double v0[8], v1[8];
+  int c0[8], c1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool on = k < a.ell.width;
+    const size_t off = static_cast<size_t>(k) * a.ell.rows;
+    v0[k] = on ? __ldg(a.ell.val + off + i0) : 0.0;
+    v1[k] = on ? __ldg(a.ell.val + off + i1) : 0.0;
+    c0[k] = on ? __ldg(a.ell.col + off + i0) : 0;
+    c1[k] = on ? __ldg(a.ell.col + off + i1) : 0;
+  }
+  double2 t0[8], t1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool on = k < a.ell.width;
+    t0[k] = on ? __ldg(reinterpret_cast<const double2*>(a.ell.x + c0[k])) : make_double2(0.0, 0.0);
+    t1[k] = on ? __ldg(reinterpret_cast<const double2*>(a.ell.x + c1[k])) : make_double2(0.0, 0.0);
+  }
+  r0 = cd{0.0, 0.0};
+  r1 = cd{0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < a.ell.width) {
+      r0.x = fma(v0[k], t0[k].x, r0.x); r0.y = fma(v0[k], t0[k].y, r0.y);
+      r1.x = fma(v1[k], t1[k].x, r1.x); r1.y = fma(v1[k], t1[k].y, r1.y);
+    }
+  }
+}
 
 // ---- solve kernels ---------------------------------------------------------------------------
 // A CTA reduces a chunk of 2^mu rows level by level.  The factor records a chunk needs do not
@@ -449,6 +508,18 @@ __device__ __forceinline__ void fwd_stage_body(const StageArgs& a, int chunk, co
   const int cnt = min(C, a.m0 - r0);
   if (a.poll_in) {
     for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = mbox_poll(a.fin + static_cast<size_t>(r0) * SB + e);
+  } else if (a.fin_is_rhs && a.ell.x != nullptr) {   // level-0 row k = entries (2k + 1) 16 ... of the right-hand side
+    // two entries per thread and round: the value / column loads of both, then the gathers of both, are in flight
+    // together (one entry at a time, the four dependent memory round trips of a thread cost the kernel 6 us)
+    const size_t base = BLK + static_cast<size_t>(r0) * SB;
+    for (int e0 = threadIdx.x; e0 < cnt * SB; e0 += 2 * NCW * 32) {
+      const int e1 = e0 + NCW * 32;
+      const bool two = e1 < cnt * SB;
+      cd r0v, r1v;
+      rhs_entry2(a, base + e0, base + (two ? e1 : e0), r0v, r1v);
+      buf0[e0] = r0v;
+      if (two) buf0[e1] = r1v;
+    }
   } else {
     for (int e = threadIdx.x; e < cnt * SB; e += NCW * 32) buf0[e] = ldcg_cd(a.fin + static_cast<size_t>(r0) * SB + e);
   }
@@ -499,11 +570,11 @@ __device__ __forceinline__ void top_stage_body(const StageArgs& a, const Ring& r
   cd* t = big + 64 * 64;
   if (tid < 64) {
     cd v{0.0, 0.0};
-    if (tid < 16) v = a.b[tid];
+    if (tid < 16) v = rhs_entry(a, tid);
     else if (TS == 64 && tid < 48) v = res[tid - 16];
     else if (tid < TS) {
       const int e = tid - (TS - 16);
-      if (a.n_pad - 1 < a.n) v = a.b[static_cast<size_t>(a.n_pad - 1) * 16 + e];
+      if (a.n_pad - 1 < a.n) v = rhs_entry(a, static_cast<size_t>(a.n_pad - 1) * 16 + e);
     }
     t[tid] = v;
   }
@@ -820,61 +891,27 @@ __device__ __forceinline__ void up_pair_backward_rhs(const BwdRegs& R, const cd*
 }
 
 // 64 x 64 unit upper triangular solve by one warp (rows lane and lane + 32), column-major with leading
-// dimension 64, diagonal slot = 1 / U_ii.  Four columns per shuffle round; branch-free (rows at or below a
-// block multiply zeros) with the next block's entries loaded before the current block's chain:
-// 3650 cycles against 8950 for the version with a divergent update (scripts/micro/trisolve.cu).
-struct TopBlk { cd p0, p1, p2, p3, q0, q1, q2, q3, u01, u02, u12, u03, u13, u23; };   // p: row lane, q: row lane + 32
-template <bool HI>
-__device__ __forceinline__ TopBlk top_load_blk(const cd* __restrict__ U, int c0, int lane) {
-  const cd* k0 = U + c0 * 64;
-  const cd z{0.0, 0.0};
-  TopBlk b;
-  const bool pa = lane < c0;
-  b.p0 = pa ? k0[lane] : z; b.p1 = pa ? k0[64 + lane] : z; b.p2 = pa ? k0[128 + lane] : z; b.p3 = pa ? k0[192 + lane] : z;
-  b.q0 = z; b.q1 = z; b.q2 = z; b.q3 = z;
-  if (HI) {
-    const bool qa = lane + 32 < c0;
-    const int i = min(lane + 32, c0);
-    b.q0 = qa ? k0[i] : z; b.q1 = qa ? k0[64 + i] : z; b.q2 = qa ? k0[128 + i] : z; b.q3 = qa ? k0[192 + i] : z;
-  }
-  b.u01 = k0[64 + c0]; b.u02 = k0[128 + c0]; b.u12 = k0[128 + c0 + 1];
-  b.u03 = k0[192 + c0]; b.u13 = k0[192 + c0 + 1]; b.u23 = k0[192 + c0 + 2];
-  return b;
-}
-template <bool HI>
-__device__ __forceinline__ void top_step_blk(const TopBlk& b, cd& y0, cd& y1, int c0, int lane) {
-  const cd src = HI ? y1 : y0;
-  const cd a0 = shfl_cd(src, c0 & 31), a1 = shfl_cd(src, (c0 + 1) & 31), a2 = shfl_cd(src, (c0 + 2) & 31),
-           x3 = shfl_cd(src, (c0 + 3) & 31);
-  cfms(y0, b.p3, x3); if (HI) cfms(y1, b.q3, x3);
-  cd x2 = a2; cfms(x2, b.u23, x3);
-  cfms(y0, b.p2, x2); if (HI) cfms(y1, b.q2, x2);
-  cd x1 = a1; cfms(x1, b.u13, x3); cfms(x1, b.u12, x2);
-  cfms(y0, b.p1, x1); if (HI) cfms(y1, b.q1, x1);
-  cd x0 = a0; cfms(x0, b.u03, x3); cfms(x0, b.u02, x2); cfms(x0, b.u01, x1);
-  cfms(y0, b.p0, x0); if (HI) cfms(y1, b.q0, x0);
-  const int j = lane - (c0 & 31);
-  cd& t = HI ? y1 : y0;
-  t = j == 0 ? x0 : t; t = j == 1 ? x1 : t; t = j == 2 ? x2 : t; t = j == 3 ? x3 : t;
-}
-// Rolled loops on purpose: this code runs once per launch on one warp, and fully unrolled it is 64 KB of
-// straight-line instructions - with a cold instruction cache (first launch after the GPU was idle) fetching them
-// cost 33 us, measured with the kernel timeline (scripts/solve_trace.py).
+// dimension 64, diagonal slot = 1 / U_ii: one column per step like unit_upper_solve (shuffle + one complex FMA per
+// row), the loop unrolled by 8 only.  History (scripts/micro/trisolve.cu and the kernel timeline): four columns per
+// shuffle round with a divergent update 8950 cycles; branch-free and fully unrolled 3650 cycles warm, but 64 KB of
+// straight-line code that runs once per launch - 33 us with a cold instruction cache; the same as rolled loops
+// 3.7 us in the kernel.
 __device__ __forceinline__ void unit_upper_solve64(const cd* __restrict__ U, cd& y0, cd& y1, int lane) {
   y0 = y0 * U[lane * 64 + lane];
   y1 = y1 * U[(lane + 32) * 64 + lane + 32];
-  TopBlk cur = top_load_blk<true>(U, 60, lane);
-#pragma unroll 1
-  for (int c0 = 60; c0 >= 32; c0 -= 4) {
-    const TopBlk nxt = top_load_blk<true>(U, c0 - 4, lane);   // c0 - 4 = 28: rows lane + 32 lie below the block, q = 0
-    top_step_blk<true>(cur, y0, y1, c0, lane);
-    cur = nxt;
+#pragma unroll 8
+  for (int k = 63; k >= 32; --k) {
+    const cd* col = U + k * 64;
+    const cd u0 = col[lane], u1 = col[min(lane + 32, k)];
+    const cd xk = shfl_cd(y1, k - 32);
+    cfms(y0, u0, xk);
+    if (lane + 32 < k) cfms(y1, u1, xk);
   }
-#pragma unroll 1
-  for (int c0 = 28; c0 >= 0; c0 -= 4) {
-    const TopBlk nxt = top_load_blk<false>(U, max(c0 - 4, 0), lane);
-    top_step_blk<false>(cur, y0, y1, c0, lane);
-    cur = nxt;
+#pragma unroll 8
+  for (int k = 31; k >= 1; --k) {
+    const cd u0 = U[k * 64 + min(lane, k)];
+    const cd xk = shfl_cd(y0, k);
+    if (lane < k) cfms(y0, u0, xk);
   }
 }
 
@@ -969,8 +1006,8 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   // the top system's boundary right-hand sides do not depend on this launch: their load overlaps the wait for the rows
   cd bvec{0.0, 0.0};
   if (top && tid < 64 && (tid < 16 || tid >= 48)) {
-    if (tid < 16) bvec = ldcg_cd(a.b + tid);
-    else if (a.n_pad - 1 < a.n) bvec = ldcg_cd(a.b + static_cast<size_t>(a.n_pad - 1) * 16 + tid - 48);
+    if (tid < 16) bvec = rhs_entry(a, tid);
+    else if (a.n_pad - 1 < a.n) bvec = rhs_entry(a, static_cast<size_t>(a.n_pad - 1) * 16 + tid - 48);
   }
   // ---- input rows
   if (tid < cnt * SB) {
@@ -1548,7 +1585,7 @@ block_matvec_kernel(int n, const cd* __restrict__ A, const cd* __restrict__ B, c
   }
 }
 
-StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const cd* b, cd* xv) {
+StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const cd* b, cd* xv, const RhsEll* ell) {
   const SluStage& st = plan.stages[s];
   StageArgs a{};
   a.l0 = st.l0; a.mu = st.mu; a.m0 = st.m0; a.nchunks = st.nchunks;
@@ -1561,6 +1598,8 @@ StageArgs make_stage_args(const SluPlan& plan, const SluDevice& d, int s, const 
   a.top = d.top;
   a.b = b;
   a.fin = s == 0 ? b + BLK : d.rhs + st.off_fin * SB;   // level-0 row k = b[(2k+1)*16 ...]
+  a.fin_is_rhs = s == 0;
+  if (ell != nullptr) a.ell = *ell;
   const bool top = s == static_cast<int>(plan.stages.size()) - 1;
   a.fout = top ? nullptr : d.rhs + plan.stages[s + 1].off_fin * SB;
   a.gvec = d.gvec;
@@ -1706,6 +1745,26 @@ static int first_upper_stage(const SluPlan& plan) {
   return sf;
 }
 
+// SMs a solve with this plan may hold while it WAITS: the CTAs of the upper-stage launch poll mailboxes written by
+// other CTAs of the same launch (all of them must be resident), and the programmatically launched first-stage kernel
+// behind it sits on its SMs until that launch completes.  One context (one stream) cannot deadlock - the launches
+// are ordered - but several contexts of one process could each get a part of their upper-stage CTAs resident and
+// wait for the rest for ever; the C ABI therefore admits concurrent solves only while the sum of their demands
+// fits the device (api.cu: SolveTicket).
+int slu_coresident_demand(const SluPlan& plan) {
+  const int ns = static_cast<int>(plan.stages.size());
+  if (ns < 2) return 1;
+  const int su = first_upper_stage(plan);
+  int ctas = 0;
+  if (su >= 0) {
+    for (int s = su; s < ns; ++s) ctas += s == ns - 1 ? 1 : plan.stages[s].nchunks;
+  } else {
+    const int sf = first_fused_stage(plan);
+    ctas = sf < ns - 1 ? plan.stages[sf].nchunks : 1;   // cooperative launch: the driver guarantees residency itself
+  }
+  return ctas + (plan.stages[0].nchunks + 2) / 3;
+}
+
 // Programmatic dependent launch of the solve's kernels: a kernel may start while its predecessor on
 // the stream is still running; it copies its first factor records (static data) and then blocks in
 // griddepcontrol.wait until the predecessor has completed.
@@ -1729,22 +1788,24 @@ static void launch_pdl(void (*kernel)(Args...), dim3 grid, dim3 block, size_t sm
 }
 
 void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
-               LaunchLog* log) {
+               LaunchLog* log, const RhsEll* ell) {
   configure_kernels();
   const int ns = static_cast<int>(plan.stages.size());
   const int su = first_upper_stage(plan);
   const int sf = su >= 0 ? su : first_fused_stage(plan);
   cd* xv = plan.n_pad == plan.n ? x : d.xpad;
   for (int s = 0; s < sf; ++s) {
-    const StageArgs a = make_stage_args(plan, d, s, b, xv);
-    log->begin(s == 0 ? LK_FWD0 : LK_FWD, stage_algo_bytes(plan, s, 7936.0));
+    const StageArgs a = make_stage_args(plan, d, s, b, xv, ell);
+    // with the B v product fused in: plus the band of B and the vector v (12 288 + 256 bytes per grid point)
+    log->begin(s == 0 ? LK_FWD0 : LK_FWD,
+               stage_algo_bytes(plan, s, 7936.0) + (s == 0 && ell != nullptr ? 12544.0 * plan.n : 0.0));
     const RingShape sh = fwd_shape(a);
     launch_pdl(slu_fwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns);
     log->end();
   }
   double top_bytes = stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2;
   if (su < 0 && sf == ns - 1) {
-    const StageArgs a = make_stage_args(plan, d, ns - 1, b, xv);
+    const StageArgs a = make_stage_args(plan, d, ns - 1, b, xv, ell);
     log->begin(LK_TOP, top_bytes);
     const RingShape sh = bwd_shape(a, true);
     slu_top_stage_kernel<<<1, RING_THREADS, sh.bytes, stream>>>(a, sh.ns, sh.nu);
@@ -1760,7 +1821,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     const size_t zoff = plan.rhs_vecs * SB;
     for (int s = sf; s < ns; ++s) {
       StageArgs& a = fst[s - sf];
-      a = make_stage_args(plan, d, s, b, xv);
+      a = make_stage_args(plan, d, s, b, xv, ell);
       if (s > sf) {            // input rows come from another CTA of this launch
         a.fin = box + plan.stages[s].off_fin * SB;
         a.poll_in = 1;
@@ -1822,7 +1883,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     log->end();
   }
   for (int s = sf - 1; s >= 0; --s) {
-    const StageArgs a = make_stage_args(plan, d, s, b, xv);
+    const StageArgs a = make_stage_args(plan, d, s, b, xv, ell);
     log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
     const RingShape sh = bwd_shape(a, false);
     launch_pdl(slu_bwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns, sh.nu);

@@ -88,6 +88,7 @@ struct SluPlan {
 };
 
 SluPlan make_slu_plan(int n, int first_stage_mu, int next_stage_mu, int top_max_rows);
+int slu_coresident_demand(const SluPlan& plan);   // SMs a running solve may hold while waiting (see slu.cu)
 
 struct SluDevice {
   const cd* A;          // (n, 3, 256) blocks
@@ -115,8 +116,18 @@ inline size_t slu_mbox_elems(const SluPlan& p) { return 2 * slu_mbox_half(p); }
 void slu_factorize(const SluPlan& plan, const SluDevice& d, cd sigma, cudaStream_t stream,
                    LaunchLog* log);
 // x = M^-1 b ; b and x are device vectors of n*16 complex (may alias)
+// With `ell` the right-hand side is b = B v, given by a compressed real-valued copy of B (bsparse.cuh) and the
+// vector v: the first-stage kernel and the top system form the entries they need themselves (same order of
+// operations as bell_matvec: bit-identical), and b is not read.  v must not alias x.
+struct RhsEll {
+  const double* val = nullptr;   // [width][rows]
+  const int32_t* col = nullptr;  // [width][rows]
+  const cd* x = nullptr;         // v; nullptr: plain right-hand side
+  int rows = 0;
+  int width = 0;                 // <= 8
+};
 void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
-               LaunchLog* log);
+               LaunchLog* log, const RhsEll* ell = nullptr);
 // y = aa * A x + ab * B x + z : covers B*x, A*x and the refinement residual
 // r = b - (A - sigma*B) x  (aa = -1, ab = sigma, z = b)
 void block_matvec(int n, const cd* A, const cd* B, cd aa, cd ab, const cd* x, const cd* z, cd* y,

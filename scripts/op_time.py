@@ -15,6 +15,6 @@ ctx.set_profiling(True)
 ctx.shift_invert(cfg, 0.02 + 0.03j, want_vectors=False)
 p = ctx.profile()
 ops = ("matvec", "fwd_stage0", "fwd_stage", "top_stage", "bwd_stage", "bwd_stage0")
-tot = sum(p[k][0] for k in ops) / max(p["matvec"][1], 1) * 1e3
+tot = sum(p[k][0] for k in ops) / max(p["fwd_stage0"][1], 1) * 1e3
 print("env", {k: v for k, v in os.environ.items() if k.startswith("LGPU_")}, "us/op %.1f" % tot,
       " ".join(f"{k}={1e3*p[k][0]/max(p[k][1],1):.1f}" for k in ops + ("cgs2_step", "dots", "update", "scale")))

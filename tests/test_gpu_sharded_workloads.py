@@ -1,0 +1,93 @@
+"""BASELINE configs 4 and 5 as lists of independent units (legolas_b200.workloads) on the device.  Needs a B200.
+
+config 5: kelvin_helmholtz_cd, G = 2001 (N = 32 016), (k2, k3) units with the per-unit shift of the coarse pre-scan, nev = 1,
+ncv = 16, maxiter = 20 - against the oracle (LAPACK zgbtrf / zgbtrs / zgbmv + SciPy's ARPACK, same parameters, same start
+vector): same number of converged pairs, eigenvalue within 1e-8 relative (north_star's tolerance), eigenvector within 1e-6
+after phase normalisation.  Units are taken from the part of the plane where the mode exists and from where it does not
+(both sides must then stop at maxiter with nothing).
+config 4: units of the 32-shift scan return the number of pairs the scan table promises, and several contexts in flight
+(host threads, one stream each) return bit-identical results to one context."""
+import warnings
+
+import numpy as np
+import pytest
+
+import legolas_b200 as lb
+from legolas_b200 import equilibria as heq
+from legolas_b200 import sweep
+from legolas_b200 import workloads as wl
+from oracle import assembly as asm
+from oracle import equilibria as oeq
+from oracle import solvers as osolvers
+
+pytestmark = pytest.mark.gpu
+
+
+def _phase_normalised(v):
+    k = int(np.argmax(np.abs(v)))
+    return v * (np.conj(v[k]) / abs(v[k])) / np.linalg.norm(v)
+
+
+# (k2, j): k3 = (j + 1) pi / 16; the first five lie in the unstable band, the last one outside it
+UNITS = [(-1.0, 15), (-1.0, 40), (-2.0, 36), (0.0, 20), (-3.0, 12), (-3.0, 30)]
+
+
+@pytest.mark.parametrize("k2,j", UNITS)
+def test_config5_unit_matches_oracle(k2, j):
+    unit = next(u for u in wl.sweep_units() if u["k2"] == k2 and abs(u["k3"] - np.pi * (j + 1) / 16) < 1e-12)
+    s, grid, fields = heq.kelvin_helmholtz_cd(wl.SWEEP_GRIDPTS, k2=unit["k2"], k3=unit["k3"])
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert", number_of_eigenvalues=wl.SWEEP_NEV,
+                                  sigma=unit["sigma"], ncv=wl.SWEEP_NCV, maxiter=wl.SWEEP_MAXITER)
+    ctx = lb.Context()
+    try:
+        mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)   # "maxiter reached" outside the unstable band
+            omega, vr, cfg, st = lb.solve_evp(mats, s)
+        vr = np.array(vr)
+    finally:
+        ctx.close()
+    so, go, xgo, fo = oeq.kelvin_helmholtz_cd_eq(gridpts=wl.SWEEP_GRIDPTS, k2=unit["k2"], k3=unit["k3"])
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    om_o, vr_o, st_o = osolvers.shift_invert(A.to_band(), B.to_band(), 31, 31, unit["sigma"], wl.SWEEP_NEV, ncv=wl.SWEEP_NCV,
+                                             maxiter=wl.SWEEP_MAXITER, return_stats=True)
+    assert st["nconv"] == st_o["nconv"], (st, st_o)
+    if st_o["nconv"] == 0:
+        assert st["info"] == 1 and np.isnan(omega[0])
+        return
+    assert abs(omega[0] - om_o[0]) <= 1e-8 * abs(om_o[0]), (omega[0], om_o[0])
+    assert omega[0].imag > 0.0                      # the unit tracks an unstable mode
+    assert abs(omega[0] - unit["coarse"]) < 0.05 * abs(unit["coarse"])   # ... the one the coarse pre-scan pointed at
+    d = np.linalg.norm(_phase_normalised(vr[:, 0]) - _phase_normalised(vr_o[:, 0]))
+    assert d <= 1e-6, d
+
+
+def test_config5_units_in_flight_are_bit_identical_to_sequential():
+    """Three contexts on three host threads (one CUDA stream each, admitted together by the library) against one context
+    solving the same units one after the other."""
+    units = wl.sweep_units(12)
+    seq = wl.SweepSolver()
+    ref = np.stack([seq(u) for u in units])
+    seq.close()
+    solvers = [wl.SweepSolver() for _ in range(3)]
+    table, mine = sweep.run_queue(units, None, wl.SWEEP_NEV, solvers=solvers)
+    for sv in solvers:
+        sv.close()
+    assert mine == list(range(len(units)))
+    assert np.array_equal(np.isnan(ref), np.isnan(table))
+    assert np.array_equal(np.nan_to_num(ref), np.nan_to_num(table))
+    assert np.isfinite(table).sum() >= 6
+
+
+def test_config4_scan_units_converge_as_tabulated():
+    solver = wl.ScanSolver()
+    try:
+        for unit in (wl.SCAN_SHIFTS[0], wl.SCAN_SHIFTS[17], wl.SCAN_SHIFTS[22], wl.SCAN_SHIFTS[31]):
+            sigma, nev, n_op = unit
+            before = solver.n_op
+            omega = solver(unit)
+            assert np.isfinite(omega).sum() == nev, (sigma, nev)
+            assert abs((solver.n_op - before) - n_op) <= 0.25 * n_op   # the cost estimate that orders the queue
+            assert np.all(np.abs(omega[:nev] - sigma) < 0.05)
+    finally:
+        solver.close()
