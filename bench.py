@@ -527,7 +527,8 @@ def run_sharded_sections(args, rank, world, local_rank, device):
     # ---- config 5: wavenumber sweep
     units = wl.sweep_units(args.sweep_units)
     workers = max(1, args.sweep_workers)
-    solvers = [wl.SweepSolver(device=local_rank) for _ in range(workers)]
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    solvers = [wl.SweepSolver(device=local_rank, sm_limit=sms // workers if workers > 1 else 0) for _ in range(workers)]
     _, cost_table, _ = timed_pass(units, list(range(len(units))), solvers, wl.SWEEP_NEV)
     # measured cost of every unit (operator applications of the untimed pass), gathered like the eigenvalues
     costs = np.full((len(units), 1), np.nan + 0j)

@@ -108,6 +108,14 @@ const char* lgpu_last_error(const lgpu_ctx* ctx);
 /* Run all work of this context on an existing CUDA stream (cudaStream_t); NULL = own stream. */
 int lgpu_set_stream(lgpu_ctx* ctx, void* cuda_stream);
 int lgpu_synchronize(lgpu_ctx* ctx);
+/* Several contexts of one process on one device (one host thread per context, e.g. a parameter sweep that keeps a few
+ * small units in flight per GPU - the reference's counterpart is the process pool of pylbo's runner,
+ * post_processing/pylbo/automation/runner.py:202-211).  Some kernels wait for other CTAs of their own launch (the
+ * fused Gram-Schmidt step has a device-wide barrier, the upper solve stages hand rows over through mailboxes), so the
+ * library admits calls of different contexts concurrently only while the SMs they may hold waiting fit the device
+ * together; a call that needs the whole device runs alone.  max_sms caps the CTAs of this context's Gram-Schmidt step
+ * (default 0: one per SM, i.e. no other context runs beside it); a sweep with k units in flight sets it to SMs / k. */
+int lgpu_set_sm_limit(lgpu_ctx* ctx, int32_t max_sms);
 
 /* ---- replaces build_matrices (src/matrices/mod_matrix_manager.f08:138-266) -----------
  * base_grid: gridpts doubles; gauss_grid: 4*(gridpts-1) doubles; fields: LGPU_N_FIELDS

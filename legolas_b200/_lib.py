@@ -67,6 +67,7 @@ SIGNATURES = {
     "lgpu_last_error": (C.c_char_p, [_P]),
     "lgpu_set_stream": (C.c_int, [_P, _P]),
     "lgpu_synchronize": (C.c_int, [_P]),
+    "lgpu_set_sm_limit": (C.c_int, [_P, C.c_int32]),
     "lgpu_assemble": (C.c_int, [_P, C.POINTER(CSettings), _P, _P, C.POINTER(_P)]),
     "lgpu_assemble_device": (C.c_int, [_P, C.POINTER(CSettings), _P, _P, C.POINTER(_P)]),
     "lgpu_matrix_dim": (C.c_int, [_P, _IP]),

@@ -233,6 +233,11 @@ class Context:
     def synchronize(self):
         self._check(self._lib.lgpu_synchronize(self._h), "synchronize")
 
+    def set_sm_limit(self, max_sms: int) -> None:
+        """Cap the CTAs of this context's fused Gram-Schmidt step (device-wide barrier) so that several contexts of
+        one process can have calls in flight on one GPU (lgpu_set_sm_limit); 0 = the whole device."""
+        self._check(self._lib.lgpu_set_sm_limit(self._h, int(max_sms)), "set_sm_limit")
+
     @property
     def dim(self) -> int:
         n = C.c_int32()

@@ -74,7 +74,8 @@ struct lgpu_ctx {
   int log_level = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  int demand_G = -1, demand = 0;   // slu_coresident_demand of the plan for G grid points (SolveTicket)
+  int demand_G = -1, demand = 0;   // SMs a call of this context may hold while waiting, for G grid points (SolveTicket)
+  int sm_limit = 0;                // lgpu_set_sm_limit: cap on the CTAs of the fused Gram-Schmidt step (0: all SMs)
   std::string err;
 
   // matrices
@@ -180,8 +181,12 @@ class SolveTicket {
 int solve_demand(lgpu_ctx* c) {
   if (c->G <= 0) return 0;
   if (c->demand_G != c->G) {
-    c->demand = slu_coresident_demand(make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 2),
-                                                    env_int("LGPU_SLU_TOP", 2)));
+    // the upper solve stages (mailboxes between their CTAs) and the fused Gram-Schmidt step (device-wide barrier)
+    // never run at the same time on one stream: the larger of the two
+    const int ntiles = (c->G * BLK + KRYLOV_TILE - 1) / KRYLOV_TILE;
+    c->demand = std::max(slu_coresident_demand(make_slu_plan(c->G, env_int("LGPU_SLU_MU0", 4), env_int("LGPU_SLU_MU1", 2),
+                                                             env_int("LGPU_SLU_TOP", 2))),
+                         krylov_cgs2_grid(ntiles, c->sm_limit));
     c->demand_G = c->G;
   }
   return c->demand;
@@ -308,6 +313,7 @@ KrylovWork kwork(lgpu_ctx* c) {
   KrylovWork w{};
   w.partial = c->kpartial.p; w.hwork = c->khwork.p; w.scal = c->kscal.p; w.ticket = c->kticket.p;
   w.gbar = c->kgbar.p; w.gbar_count = &c->kgbar_count;
+  w.grid_cap = c->sm_limit;
   return w;
 }
 
@@ -744,6 +750,13 @@ int lgpu_set_stream(lgpu_ctx* ctx, void* cuda_stream) {
     }
     return LGPU_OK;
   });
+}
+
+int lgpu_set_sm_limit(lgpu_ctx* ctx, int32_t max_sms) {
+  if (!ctx || max_sms < 0) return LGPU_EINVAL;
+  ctx->sm_limit = max_sms;
+  ctx->demand_G = -1;
+  return LGPU_OK;
 }
 
 int lgpu_synchronize(lgpu_ctx* ctx) {

@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   const int sstride = (ncopy + 1) * PASS_T;
   cd* buf = reinterpret_cast<cd*>(smem_raw);                            // [nstages][sstride]
   cd* wkeep = buf + static_cast<size_t>(nstages) * sstride;              // [tiles_max][64]
-  cd* part = wkeep + static_cast<size_t>(a.tiles_max) * PASS_T;          // [2][4][64]
-  cd* hs = part + 2 * PASS_GROUPS * PASS_T;                             // [KRYLOV_PASS_MAXCOL]
+  cd* part = wkeep + static_cast<size_t>(a.tiles_max) * PASS_T;          // [2][2][4][64]
+  cd* hs = part + 4 * PASS_GROUPS * PASS_T;                             // [KRYLOV_PASS_MAXCOL]
   uint64_t* full = reinterpret_cast<uint64_t*>(hs + KRYLOV_PASS_MAXCOL);
   uint64_t* empty = full + nstages;
   __shared__ double red[8];
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
 
   const SmallDiv csd{nstages, 65536 / nstages + 1};
   // local tile i of pass `pass` -> registers (see the producer for the slot / residency rules)
-  auto load_tile = [&](int pass, int i, bool want_w, cd& wi) {
+  auto load_tile_into = [&](cd (&v)[NJ], int pass, int i, bool want_w, cd& wi) {
     const int S = nstages, sg = csd.mod(i);
     const bool valid = (t0 + i) * PASS_T + r < L.n;
     const bool resident = (pass == 2 && i >= nt - S) || (pass == 3 && i < S);
@@ -388,6 +388,31 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     __syncwarp();
     if (!keep && lane == 0) mbar_arrive(&empty[sg]);
   };
+  auto load_tile = [&](int pass, int i, bool want_w, cd& wi) { load_tile_into(v, pass, i, want_w, wi); };
+  // Two tiles per CTA barrier (passes 2 and 3 of the predicate-free variants): the chain of a tile - registers,
+  // partial sums, exchange through shared memory, barrier, corrected w - is latency, not work (2.6 k cycles per tile
+  // in pass 2 against 1.2 k cycles per tile of arrival); two independent chains share one barrier.  Same operations
+  // per entry in the same order as one tile at a time.
+  cd v2[NJ];
+  auto correct_pair = [&](int ia, int ib, cd& wa, cd& wb) {
+    cd pa0{0.0, 0.0}, pa1{0.0, 0.0}, pb0{0.0, 0.0}, pb1{0.0, 0.0};
+    const cd* hq = hs + q * NJ;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const cd hj = hq[j];
+      if (j & 1) { cfma(pa1, v[j], hj); cfma(pb1, v2[j], hj); }
+      else { cfma(pa0, v[j], hj); cfma(pb0, v2[j], hj); }
+    }
+    cd* pp = part + flip * 2 * PASS_GROUPS * PASS_T;
+    flip ^= 1;
+    pp[q * PASS_T + r] = pa0 + pa1;
+    pp[(PASS_GROUPS + q) * PASS_T + r] = pb0 + pb1;
+    const cd wolda = wkeep[ia * PASS_T + r], woldb = wkeep[ib * PASS_T + r];
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const cd* pb = pp + PASS_GROUPS * PASS_T;
+    wa = wolda - ((pp[r] + pp[PASS_T + r]) + (pp[2 * PASS_T + r] + pp[3 * PASS_T + r]));
+    wb = woldb - ((pb[r] + pb[PASS_T + r]) + (pb[2 * PASS_T + r] + pb[3 * PASS_T + r]));
+  };
   // w_r -= sum_c V(r, c) hs[c] from the registers of the four column groups of row r
   auto correct = [&](int i) -> cd {
     cd p0{0.0, 0.0}, p1{0.0, 0.0};
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         }
       }
     }
-    cd* pp = part + flip * PASS_GROUPS * PASS_T;
+    cd* pp = part + flip * 2 * PASS_GROUPS * PASS_T;
     flip ^= 1;
     pp[q * PASS_T + r] = p0 + p1;
     const cd wold = wkeep[i * PASS_T + r];
@@ -459,7 +484,27 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   double nrm = 0.0;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) acc[j] = cd{0.0, 0.0};
-  for (int i = nt - 1; i >= 0; --i) {
+  int i2 = nt - 1;
+  if (EXACT) {
+    for (; i2 >= 1; i2 -= 2) {
+      cd wa{0.0, 0.0}, wb{0.0, 0.0};
+      load_tile_into(v, 2, i2, false, wa);
+      load_tile_into(v2, 2, i2 - 1, false, wb);
+      correct_pair(i2, i2 - 1, wa, wb);
+      if ((t0 + i2) * PASS_T + r >= L.n) wa = cd{0.0, 0.0};
+      if (q == 0) {
+        wkeep[i2 * PASS_T + r] = wa;
+        nrm += abs2(wa);
+        wkeep[(i2 - 1) * PASS_T + r] = wb;
+        nrm += abs2(wb);
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) cfmac(acc[j], v[j], wa);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) cfmac(acc[j], v2[j], wb);
+    }
+  }
+  for (int i = i2; i >= 0; --i) {
     cd wi{0.0, 0.0};
     load_tile(2, i, false, wi);
     wi = correct(i);
@@ -505,10 +550,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
 
   // ---- pass 3: w -= V s, and the next basis vector V(:, newcol) = vplain = w / ||w|| on the way
   const double inv = 1.0 / rnorm;
-  for (int i = 0; i < nt; ++i) {
-    cd wi{0.0, 0.0};
-    load_tile(3, i, false, wi);
-    wi = correct(i);
+  auto emit = [&](int i, cd wi) {
     if (q == 0) {
       const int gi = (t0 + i) * PASS_T + r;
       if (gi < L.n) {
@@ -520,6 +562,23 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         }
       }
     }
+  };
+  int i3 = 0;
+  if (EXACT) {
+    for (; i3 + 1 < nt; i3 += 2) {
+      cd wa{0.0, 0.0}, wb{0.0, 0.0};
+      load_tile_into(v, 3, i3, false, wa);
+      load_tile_into(v2, 3, i3 + 1, false, wb);
+      correct_pair(i3, i3 + 1, wa, wb);
+      emit(i3, wa);
+      emit(i3 + 1, wb);
+    }
+  }
+  for (int i = i3; i < nt; ++i) {
+    cd wi{0.0, 0.0};
+    load_tile(3, i, false, wi);
+    wi = correct(i);
+    emit(i, wi);
   }
 }
 
@@ -773,7 +832,7 @@ void krylov_update(const BasisLayout& L, const cd* V, int ncols, cd* w, const Kr
 constexpr size_t CGS2_SMEM_MAX = 225 * 1024;
 static size_t cgs2_smem(int ncols, int nstages, int tiles_max) {
   return sizeof(cd) * (static_cast<size_t>(nstages) * (ncols + 1) * PASS_T + static_cast<size_t>(tiles_max) * PASS_T +
-                       2 * PASS_GROUPS * PASS_T + KRYLOV_PASS_MAXCOL) + 16 * nstages;
+                       4 * PASS_GROUPS * PASS_T + KRYLOV_PASS_MAXCOL) + 16 * nstages;
 }
 
 template <int CPG>
@@ -788,11 +847,16 @@ static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t st
                                          args, smem, stream));
 }
 
+int krylov_cgs2_grid(int ntiles, int grid_cap) {
+  const int sms = grid_cap > 0 ? std::min(grid_cap, sm_count()) : sm_count();
+  return std::max(1, std::min(sms, ntiles));
+}
+
 bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const KrylovWork& work, cd* Hcol,
                       int newcol, cd* vplain, cd* hsub, cudaStream_t stream, LaunchLog* log) {
   static const bool enabled = [] { const char* e = std::getenv("LGPU_CGS2_FUSED"); return !(e && e[0] == '0'); }();
   static const bool exact_ok = [] { const char* e = std::getenv("LGPU_CGS2_EXACT"); return !(e && e[0] == '0'); }();
-  const int grid = std::max(1, std::min(sm_count(), L.ntiles));
+  const int grid = krylov_cgs2_grid(L.ntiles, work.grid_cap);
   const int tiles_max = (L.ntiles + grid - 1) / grid;
   // columns-per-group variants without per-column predicates: they stream 4 * cpg <= ncv columns
   const int cpg = (ncols + PASS_GROUPS - 1) / PASS_GROUPS;

@@ -44,7 +44,10 @@ struct KrylovWork {
   unsigned int* ticket;
   unsigned long long* gbar;         // device-wide barrier counter of the fused step kernel (or null)
   unsigned long long* gbar_count;   // host: value the counter will have when the next launch starts
+  int grid_cap = 0;                 // > 0: the fused step kernel uses at most this many CTAs (lgpu_set_sm_limit)
 };
+// CTAs of the fused step kernel (one per SM, all of them must be resident: it has a device-wide barrier)
+int krylov_cgs2_grid(int ntiles, int grid_cap);
 
 // h = V(:, 0:ncols)^H w  -> work.hwork ; Hcol (device, may be null) gets `=` (accumulate == 0)
 // or `+=` (accumulate == 1).

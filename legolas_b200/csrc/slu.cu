@@ -1380,17 +1380,25 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     }
   }
   __syncthreads();
-  // ... and their place takes X = L11^-1 (unit lower triangular), one column per thread
-  if (tid < SB) {
-    const int c = tid;
-    for (int i = 0; i < SB; ++i) {
-      cd v{i == c ? 1.0 : 0.0, 0.0};
-      if (i > c) {
-        v = cd{0.0, 0.0};
-        for (int j = c; j < i; ++j) cfms(v, W[i * WLD + j], X[j * WLD + c]);
+  // ... and their place takes X = L11^-1 (unit lower triangular).  Column sweep: warp w owns columns 4w .. 4w + 3,
+  // lane = row; once x_j is final it is broadcast and every row below subtracts L(i, j) x_j - the same subtractions
+  // in the same order as forward substitution row by row (bit-identical), but 32 dependent steps per column instead
+  // of 496 (one thread per column before: 13 us of the ~83 us a merge takes).
+  {
+    const int c0 = 4 * rg;
+    cd v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = cd{lane == c0 + q ? 1.0 : 0.0, 0.0};
+    for (int j = c0; j < SB - 1; ++j) {
+      const cd lij = lane > j ? W[lane * WLD + j] : cd{0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const cd xj = cd{__shfl_sync(0xffffffffu, v[q].x, j), __shfl_sync(0xffffffffu, v[q].y, j)};
+        if (lane > j && j >= c0 + q) cfms(v[q], lij, xj);
       }
-      X[i * WLD + c] = (i >= c) ? v : cd{0.0, 0.0};
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) X[lane * WLD + c0 + q] = lane >= c0 + q ? v[q] : cd{0.0, 0.0};
   }
   __syncthreads();
   // M2 = L21 L11^-1 over L21 (rows 32..63, columns 0..31 of W): thread (i, 4 columns)

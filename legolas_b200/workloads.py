@@ -103,9 +103,11 @@ class SweepSolver:
     """One library context; ``solve(unit)`` samples the equilibrium of the unit's (k2, k3), assembles, factorises
     and tracks the mode next to the unit's shift (nev = 1, ncv = 16, at most 20 restarts)."""
 
-    def __init__(self, device: int = 0, gridpts: int = SWEEP_GRIDPTS):
+    def __init__(self, device: int = 0, gridpts: int = SWEEP_GRIDPTS, sm_limit: int = 0):
         self.gridpts = gridpts
         self.ctx = api.Context(device=device)
+        if sm_limit:
+            self.ctx.set_sm_limit(sm_limit)   # share of the GPU when several units are in flight
         self.n_op = 0
         self.converged = 0
 

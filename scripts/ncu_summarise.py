@@ -18,7 +18,7 @@ KIND_OF = [  # kernel name prefix -> bench.py kernel-class name (api.cu LaunchKi
     ("krylov_cgs2", "cgs2_step"), ("krylov_pass_kernel<0, 1>", "dots"), ("krylov_pass_kernel<1, 1>", "dots"),
     ("krylov_pass_kernel<1, 0>", "update"), ("krylov_scale", "scale"),
     ("basis_gemm", "gemm"), ("block_matvec", "matvec"), ("bell_matvec", "matvec"), ("slu_fwd_stage", "fwd_stage"),
-    ("slu_bwd_stage", "bwd_stage"), ("slu_top_stage", "top_stage"), ("slu_fused_stage", "top_stage"),
+    ("slu_bwd_stage", "bwd_stage"), ("slu_top_stage", "top_stage"), ("slu_fused_stage", "top_stage"), ("slu_upper", "top_stage"),
     ("slu_merge", "factor"),
     ("slu_build_rows", "factor"), ("slu_top_factor", "factor"), ("assemble", "assemble"),
     ("boundary", "assemble"),

@@ -69,7 +69,7 @@ def test_config5_units_in_flight_are_bit_identical_to_sequential():
     seq = wl.SweepSolver()
     ref = np.stack([seq(u) for u in units])
     seq.close()
-    solvers = [wl.SweepSolver() for _ in range(3)]
+    solvers = [wl.SweepSolver(sm_limit=148 // 3) for _ in range(3)]
     table, mine = sweep.run_queue(units, None, wl.SWEEP_NEV, solvers=solvers)
     for sv in solvers:
         sv.close()
