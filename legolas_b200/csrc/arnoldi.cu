@@ -641,6 +641,77 @@ basis_gemm_rows_kernel(BasisLayout L, const cd* V, int nk, const cd* __restrict_
   }
 }
 
+// Restart / extraction GEMM on the FP64 tensor cores (mma.sync.m8n8k4.f64): Out(64 rows of a tile, nc) = V(tile, nk) Q.
+// The DMMA pipe is no faster than DFMA on this GPU (37 vs 35 TFLOP/s, profiles/fp64_pipe_r1.md) - the point is the
+// instruction count: the row-per-thread kernel above issues one broadcast shared-memory load per complex FMA and
+// reaches ~36 % of the FP64 peak (99 us for 1.2 GFLOP); here a warp owns 8 rows, its A fragments (one complex value
+// per lane and k-step) are reused for every block of 8 output columns, and one shared-memory load feeds four MMAs
+// (real / imaginary x real / imaginary).  Persistent CTAs, Q staged once per CTA, one 64-row tile (contiguous in the
+// basis layout) at a time; in place is safe (the tile is in shared memory before the first store).
+//   smem: A [nkp][A_LD] complex (A_LD = 66: the 8 lanes of a quarter warp hit 8 different 16-byte bank groups),
+//         Q [ncp][nkp + 4] complex (same reason), nkp / ncp = nk / nc rounded up to 4 / 8
+constexpr int GEMM_A_LD = PASS_T + 2;
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+template <int NBLK>   // blocks of 8 output columns
+__global__ void __launch_bounds__(256)
+basis_gemm_mma_kernel(BasisLayout L, const cd* V, int nk, const cd* __restrict__ Q, int ldq, int nc, cd* Out,
+                      int out_plain_ld) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nkp = (nk + 3) & ~3, qld = nkp + 4;
+  cd* As = reinterpret_cast<cd*>(smem_raw);          // [nkp][GEMM_A_LD]
+  cd* Qs = As + nkp * GEMM_A_LD;                     // [8 NBLK][qld]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < 8 * NBLK * qld; e += 256) {
+    const int c = e / qld, j = e - c * qld;
+    Qs[e] = (c < nc && j < nk) ? Q[static_cast<size_t>(c) * ldq + j] : cd{0.0, 0.0};
+  }
+  for (int e = tid; e < (nkp - nk) * PASS_T; e += 256) As[(nk + e / PASS_T) * GEMM_A_LD + (e % PASS_T)] = cd{0.0, 0.0};
+  const int g = lane >> 2, q4 = lane & 3;            // fragment coordinates: row / column group, k index
+  for (int t = blockIdx.x; t < L.ntiles; t += gridDim.x) {
+    const cd* src = V + static_cast<size_t>(t) * L.ncv * PASS_T;
+    __syncthreads();                                 // the previous tile's fragments have been read
+    for (int e = tid; e < nk * PASS_T; e += 256) {
+      const double2 v = *reinterpret_cast<const double2*>(src + e);
+      As[(e >> 6) * GEMM_A_LD + (e & 63)] = cd{v.x, v.y};
+    }
+    __syncthreads();
+    double cr[NBLK][2], ci[NBLK][2];
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) { cr[b][0] = cr[b][1] = ci[b][0] = ci[b][1] = 0.0; }
+    const cd* arow = As + q4 * GEMM_A_LD + 8 * warp + g;
+    const cd* qrow = Qs + g * qld + q4;
+    for (int ks = 0; ks < nkp; ks += 4) {
+      const cd a = arow[ks * GEMM_A_LD];
+      const double nai = -a.y;
+#pragma unroll
+      for (int b = 0; b < NBLK; ++b) {
+        const cd q = qrow[8 * b * qld + ks];
+        dmma_884(cr[b][0], cr[b][1], a.x, q.x);
+        dmma_884(cr[b][0], cr[b][1], nai, q.y);
+        dmma_884(ci[b][0], ci[b][1], a.x, q.y);
+        dmma_884(ci[b][0], ci[b][1], a.y, q.x);
+      }
+    }
+    // C fragment: row g of the warp's 8, columns 8 b + 2 q4 + {0, 1}
+    const int r = 8 * warp + g, gi = t * PASS_T + r;
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = 8 * b + 2 * q4 + h;
+        if (c < nc && gi < L.n) {
+          const cd v{cr[b][h], ci[b][h]};
+          if (out_plain_ld > 0) Out[static_cast<size_t>(c) * out_plain_ld + gi] = v;
+          else Out[(static_cast<size_t>(t) * L.ncv + c) * PASS_T + r] = v;
+        }
+      }
+    }
+  }
+}
+
 // 32 consecutive rows (inside one tile: T is a multiple of 32) per CTA.
 __global__ void __launch_bounds__(256)
 basis_gemm_kernel(BasisLayout L, const cd* __restrict__ V, int nk, const cd* __restrict__ Q,
@@ -908,7 +979,28 @@ void basis_gemm(const BasisLayout& L, const cd* V, int nk, const cd* Q, int ldq,
   });
   log->begin(LK_GEMM, 16.0 * L.n * (nk + nc));
   static const bool rows_path = [] { const char* e = std::getenv("LGPU_GEMM_ROWS"); return !(e && e[0] == '0'); }();
-  if (rows_path && nk <= 40 && sizeof(cd) * nk * nc <= 48 * 1024)
+  static const bool mma_path = [] { const char* e = std::getenv("LGPU_GEMM_MMA"); return !(e && e[0] == '0'); }();
+  const int nkp = (nk + 3) & ~3, nblk = (nc + 7) / 8;
+  const size_t mma_smem = sizeof(cd) * (static_cast<size_t>(nkp) * GEMM_A_LD + static_cast<size_t>(8 * nblk) * (nkp + 4));
+  if (mma_path && L.T == PASS_T && nblk >= 1 && nblk <= 5 && nk <= 64 && mma_smem <= 100 * 1024) {
+    static PerDeviceOnce once_mma;
+    once_mma.run([] {
+      CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(basis_gemm_mma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    });
+    const int per_sm = std::max(1, std::min(3, static_cast<int>((220 * 1024) / (mma_smem + 1024))));
+    const int grid = std::max(1, std::min(L.ntiles, per_sm * sm_count()));
+    switch (nblk) {
+      case 1: basis_gemm_mma_kernel<1><<<grid, 256, mma_smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld); break;
+      case 2: basis_gemm_mma_kernel<2><<<grid, 256, mma_smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld); break;
+      case 3: basis_gemm_mma_kernel<3><<<grid, 256, mma_smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld); break;
+      case 4: basis_gemm_mma_kernel<4><<<grid, 256, mma_smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld); break;
+      default: basis_gemm_mma_kernel<5><<<grid, 256, mma_smem, stream>>>(L, V, nk, Q, ldq, nc, Out, out_plain_ld); break;
+    }
+  } else if (rows_path && nk <= 40 && sizeof(cd) * nk * nc <= 48 * 1024)
     basis_gemm_rows_kernel<40><<<(L.n + 127) / 128, 128, sizeof(cd) * nk * nc, stream>>>(L, V, nk, Q, ldq, nc, Out,
                                                                                          out_plain_ld);
   else

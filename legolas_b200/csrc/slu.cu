@@ -424,6 +424,46 @@ __device__ __forceinline__ cd unit_upper_solve(const cd* U, cd r, int lane) {
   return r;
 }
 
+// Variant for the latency-bound upper stages (one substitution at a time per SM): two columns per shuffle round,
+// masked coefficients - lane i multiplies column c by U(i, c) if i < c and by zero otherwise, so the lanes of the
+// block get their own unknown from the same update as the rows above (no select, no branch) - and the next block's
+// entries loaded ahead.  Same subtractions in the same order per entry (bit-identical); 1390 cycles against 1540
+// (scripts/micro/trisolve.cu).  The diagonal and the first block do not depend on the right-hand side: the caller
+// fetches them while it waits for it (UpperPre).
+struct UpperPre { cd dinv, w0, w1, u01; };
+__device__ __forceinline__ void upper_blk2_load(const cd* __restrict__ U, int c0, int lane, cd& w0, cd& w1, cd& u01) {
+  const cd* col0 = U + tri_up_off(c0);
+  const cd* col1 = U + tri_up_off(c0 + 1);
+  const cd z{0.0, 0.0};
+  const cd a = col0[min(lane, c0)], b = col1[min(lane, c0 + 1)];
+  w0 = lane < c0 ? a : z;
+  w1 = lane < c0 + 1 ? b : z;
+  u01 = col1[c0];
+}
+__device__ __forceinline__ UpperPre unit_upper_prefetch(const cd* __restrict__ U, int lane) {
+  UpperPre p;
+  p.dinv = U[tri_up_off(lane) + lane];
+  upper_blk2_load(U, SB - 2, lane, p.w0, p.w1, p.u01);
+  return p;
+}
+__device__ __forceinline__ cd unit_upper_solve2(const cd* __restrict__ U, const UpperPre& p, cd r, int lane) {
+  r = r * p.dinv;
+  cd w0 = p.w0, w1 = p.w1, u01 = p.u01;
+#pragma unroll
+  for (int kb = SB / 2 - 1; kb >= 0; --kb) {
+    const int c0 = 2 * kb;
+    cd n0 = w0, n1 = w1, n01 = u01;
+    if (kb > 0) upper_blk2_load(U, c0 - 2, lane, n0, n1, n01);
+    cd x0 = shfl_cd(r, c0);
+    const cd x1 = shfl_cd(r, c0 + 1);
+    cfms(r, w1, x1);
+    cfms(x0, u01, x1);
+    cfms(r, w0, x0);
+    w0 = n0; w1 = n1; u01 = n01;
+  }
+  return r;
+}
+
 // z slots 0 and cnt hold the known end unknowns; fill in the interior ones.
 //   z = U^-1 (g - E z_left - F z_right) per merged pair, upper levels first
 __device__ __forceinline__ void chunk_backward(const StageArgs& a, const Ring& rg, RingPos& pos,
@@ -987,6 +1027,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
   const bool hasA = grp < np0, hasB = grp == 0 && np1 > 0;
   FwdRegs FA, FB;
   BwdRegs BA, BB;
+  UpperPre preA, preB;
   if (hasA) { mbar_wait(&bars[2 * grp], 0u); load_fwd(recs + grp * PAIR_STRIDE, t, FA); }
   if (hasB) { mbar_wait(&bars[2 * np0], 0u); load_fwd(recs + np0 * PAIR_STRIDE, t, FB); }
   // dense top system: thread = (row, 16 columns) of Linv; the top CTA has no second-level pair, so the entries
@@ -1049,6 +1090,10 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
     // the matrices of the back substitution take the place of the forward ones while the unknowns are on their way
     if (hasA) { mbar_wait(&bars[2 * grp + 1], 0u); load_bwd(recs + grp * PAIR_STRIDE, t, BA); }
     if (hasB) { mbar_wait(&bars[2 * np0 + 1], 0u); load_bwd(recs + np0 * PAIR_STRIDE, t, BB); }
+    if (t < 32) {   // the solver warp of the group: what the substitutions need before their right-hand sides exist
+      if (hasA) preA = unit_upper_prefetch(recs + grp * PAIR_STRIDE + PR_U, lane);
+      if (hasB) preB = unit_upper_prefetch(recs + np0 * PAIR_STRIDE + PR_U, lane);
+    }
     // boundary unknowns of the chunk
     if (tid < 2 * SB) {
       const bool right = tid >= SB;
@@ -1070,7 +1115,11 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
       }
       part[cg * 64 + row] = p0 + p1;
     }
-    if (hasA) { mbar_wait(&bars[2 * grp + 1], 0u); load_bwd(recs + grp * PAIR_STRIDE, t, BA); }
+    if (hasA) {
+      mbar_wait(&bars[2 * grp + 1], 0u);
+      load_bwd(recs + grp * PAIR_STRIDE, t, BA);
+      if (t < 32) preA = unit_upper_prefetch(recs + grp * PAIR_STRIDE + PR_U, lane);
+    }
     __syncthreads();
     TRACE_MARK(1, 13);
     if (tid < 32) {
@@ -1094,7 +1143,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
     group_sync(0);
     TRACE_MARK(1, 11);
     if (t < 32) {
-      const cd x = unit_upper_solve(recs + np0 * PAIR_STRIDE + PR_U, rbuf[lane], lane);
+      const cd x = unit_upper_solve2(recs + np0 * PAIR_STRIDE + PR_U, preB, rbuf[lane], lane);
       z[2 * SB + lane] = x;
       publish_node(a, unknown_index(a, r0 + 2), lane, x);
     }
@@ -1109,7 +1158,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) slu_upper_kernel(const __grid_c
     up_pair_backward_rhs(BA, z + ql * SB, z + qr * SB, gA, rbuf + grp * SB, t);
     group_sync(grp);
     if (t < 32) {
-      const cd x = unit_upper_solve(recs + grp * PAIR_STRIDE + PR_U, rbuf[grp * SB + lane], lane);
+      const cd x = unit_upper_solve2(recs + grp * PAIR_STRIDE + PR_U, preA, rbuf[grp * SB + lane], lane);
       z[qm * SB + lane] = x;
       publish_node(a, unknown_index(a, r0 + qm), lane, x);
     }
@@ -1525,15 +1574,35 @@ __global__ void __launch_bounds__(256) slu_top_factor_kernel(FactorArgs a) {
     }
     __syncthreads();
   }
-  if (tid < 64) {
-    const int c = tid;
-    for (int i = 0; i < 64; ++i) {
-      cd v{i == c ? 1.0 : 0.0, 0.0};
-      if (i > c && i < TS && c < TS) {
-        v = cd{0.0, 0.0};
-        for (int j = c; j < i; ++j) cfms(v, W[i * TLD + j], X[j * TLD + c]);
+  // X = L^-1 by a warp-parallel column sweep (see slu_merge_kernel): warp w owns columns 8w .. 8w + 7, a lane holds
+  // rows lane and lane + 32; same subtractions in the same order as row-by-row forward substitution.  One thread per
+  // column took ~85 us of this kernel's 185 us (2016 dependent complex FMAs with a shared-memory load each).
+  {
+    const int lane = tid & 31, c0 = 8 * (tid >> 5);
+    cd v0[8], v1[8];   // rows lane, lane + 32
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v0[q] = cd{lane == c0 + q ? 1.0 : 0.0, 0.0};
+      v1[q] = cd{lane + 32 == c0 + q ? 1.0 : 0.0, 0.0};
+    }
+    for (int j = c0; j < TS - 1; ++j) {
+      const cd l0 = lane > j ? W[lane * TLD + j] : cd{0.0, 0.0};
+      const cd l1 = (lane + 32 > j && lane + 32 < TS) ? W[(lane + 32) * TLD + j] : cd{0.0, 0.0};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const cd src = j < 32 ? v0[q] : v1[q];
+        const cd xj = cd{__shfl_sync(0xffffffffu, src.x, j & 31), __shfl_sync(0xffffffffu, src.y, j & 31)};
+        if (j >= c0 + q) {
+          if (lane > j) cfms(v0[q], l0, xj);
+          if (lane + 32 > j && lane + 32 < TS) cfms(v1[q], l1, xj);
+        }
       }
-      X[i * TLD + c] = (i >= c) ? v : cd{0.0, 0.0};
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = c0 + q;
+      X[lane * TLD + c] = lane >= c ? v0[q] : cd{0.0, 0.0};
+      X[(lane + 32) * TLD + c] = lane + 32 >= c ? v1[q] : cd{0.0, 0.0};
     }
   }
   __syncthreads();

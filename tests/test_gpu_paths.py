@@ -58,7 +58,10 @@ def default_result():
     {"LGPU_CGS2_FUSED": "0"},                    # three Gram-Schmidt pass kernels + scale
     {"LGPU_CGS2_EXACT": "0"},                    # fused step kernel with per-column predicates only
     {"LGPU_B_ELL": "0"},                         # dense block product for B x
-    {"LGPU_GEMM_ROWS": "0"},                     # shared-memory tiled restart GEMM
+    {"LGPU_GEMM_MMA": "0"},                      # restart GEMM with one row per thread instead of the FP64 MMA kernel
+    {"LGPU_GEMM_MMA": "0", "LGPU_GEMM_ROWS": "0"},   # shared-memory tiled restart GEMM
+    {"LGPU_SLU_UPPER": "0"},                     # upper solve stages streamed through rings (cooperative launch)
+    {"LGPU_BX_FUSE": "0"},                       # separate launch for the B x product
     {"LGPU_SLU_MU0": "3", "LGPU_SLU_MU1": "3", "LGPU_SLU_TOP": "32"},  # another stage tree
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_matches_default(default_result, env_extra):
