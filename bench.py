@@ -373,6 +373,15 @@ def run_gpu(args):
     else:
         gathered = [per_rank]
 
+    # the operator application as the Arnoldi driver issues it: 200 applications back to back on the factors of the last
+    # step, one CUDA-event pair around the batch (the per-launch event pairs of the instrumented pass serialise the
+    # programmatic dependent launches, so the sum of their kernel times overstates the application)
+    d_x = torch.randn(2 * n, dtype=torch.float64, device=device)
+    d_y = torch.empty_like(d_x)
+    torch.cuda.synchronize()
+    ctx.apply_op_device(d_x.data_ptr(), d_y.data_ptr(), repeat=20)
+    op_us_batch = 1e3 * ctx.apply_op_device(d_x.data_ptr(), d_y.data_ptr(), repeat=200)
+
     sharded = None
     if not args.no_sharded:
         sharded = run_sharded_sections(args, rank, world, local_rank, device)
@@ -432,9 +441,14 @@ def run_gpu(args):
                               "ms_in_kernels_per_step": round(kernel_ms, 3),
                               "ms_outside_kernels_per_step": round(1e3 * sec_per_step - kernel_ms, 3)},
             "op_roofline": {"what": "whole OP*x = (A - sigma B)^-1 B x (3 launches: forward stage 0 with the B x product fused in, upper stages + top system, backward stage 0), 37120*G algorithmic bytes",
-                            "achieved": round(op_gbs, 1) if op_gbs else None, "unit": "GB/s",
-                            "frac": round(op_gbs / peak, 4) if op_gbs else None,
-                            "us_per_op": round(1e3 * op_ms / max(n_op_total, 1), 2)},
+                            "achieved": round(37120.0 * GRIDPTS / (op_us_batch * 1e-6) / 1e9, 1), "unit": "GB/s",
+                            "frac": round(37120.0 * GRIDPTS / (op_us_batch * 1e-6) / 1e9 / peak, 4),
+                            "us_per_op": round(op_us_batch, 2),
+                            "how": "200 applications back to back, one CUDA-event pair around the batch",
+                            "sum_of_kernel_events": {"achieved": round(op_gbs, 1) if op_gbs else None,
+                                                     "frac": round(op_gbs / peak, 4) if op_gbs else None,
+                                                     "us_per_op": round(1e3 * op_ms / max(n_op_total, 1), 2),
+                                                     "note": "per-launch event pairs: no overlap between launches"}},
             "kernels": kernel_table,
             "ms_per_step_with_launch_events": round(1e3 * t_prof / args.steps, 3),
             "phases_ms": ctx.phase_times(),

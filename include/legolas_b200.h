@@ -151,6 +151,13 @@ int lgpu_factorize(lgpu_ctx* ctx, double sigma_re, double sigma_im, int32_t* lu_
 int lgpu_solve(lgpu_ctx* ctx, const double* rhs_ri, double* x_ri, int32_t refine_steps);
 int lgpu_matvec(lgpu_ctx* ctx, int32_t which, const double* x_ri, double* y_ri);
 int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refine_steps);
+/* The same step with device-resident vectors, `repeat` times back to back on the context's stream (every application
+ * reads x_dev and writes y_dev; x_dev != y_dev), as the Arnoldi driver issues it; *ms_per_application (may be NULL) =
+ * CUDA-event time of the batch / repeat.  This is how the operator application is timed for the roofline: event pairs
+ * around single launches serialise the programmatic dependent launches that overlap a kernel's prologue with its
+ * predecessor. */
+int lgpu_apply_op_device(lgpu_ctx* ctx, const double* x_dev, double* y_dev, int32_t refine_steps, int32_t repeat,
+                         double* ms_per_application);
 
 /* ---- replaces solve_arpack_shift_invert (smod_arpack_shift_invert.f08:15-161) ---------
  * resid0_ri: start vector (N complex) = zlarnv(2, [2022,9,30,179], N) from the host

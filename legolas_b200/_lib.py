@@ -78,6 +78,7 @@ SIGNATURES = {
     "lgpu_solve": (C.c_int, [_P, _P, _P, C.c_int32]),
     "lgpu_matvec": (C.c_int, [_P, C.c_int32, _P, _P]),
     "lgpu_apply_op": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "lgpu_apply_op_device": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _DP]),
     "lgpu_shift_invert": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),
     "lgpu_shift_invert_device": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),
     "lgpu_arnoldi_general": (C.c_int, [_P, C.POINTER(CArnoldi), _P, _P, _P, C.POINTER(CStats)]),

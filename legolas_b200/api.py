@@ -372,6 +372,14 @@ class Context:
         self._check(self._lib.lgpu_apply_op(self._h, x.ctypes.data, y.ctypes.data, refine_steps), "apply_op")
         return y
 
+    def apply_op_device(self, x_ptr: int, y_ptr: int, repeat: int = 1, refine_steps: int = 0) -> float:
+        """``repeat`` operator applications y = (A - sigma B)^-1 B x on device vectors (raw pointers), back to back;
+        returns the CUDA-event time per application in milliseconds (lgpu_apply_op_device)."""
+        ms = C.c_double(0.0)
+        self._check(self._lib.lgpu_apply_op_device(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), refine_steps, repeat,
+                                                   C.byref(ms)), "apply_op_device")
+        return ms.value
+
     # ---- the eigen-solve
     def arnoldi_general(self, cfg: ArpackConfig, refine_steps: int = 0, want_vectors: bool = True):
         """solve_arpack_general (src/solvers/arnoldi/smod_arpack_general.f08:14-131): ARPACK on

@@ -996,6 +996,25 @@ int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refin
   });
 }
 
+int lgpu_apply_op_device(lgpu_ctx* ctx, const double* x_dev, double* y_dev, int32_t refine_steps, int32_t repeat,
+                         double* ms_per_application) {
+  return guarded(ctx, [&] {
+    if (!ctx->factorized) return fail(ctx, LGPU_ESTATE, "apply_op_device: call lgpu_factorize first");
+    if (!x_dev || !y_dev || x_dev == y_dev || repeat < 1) return fail(ctx, LGPU_EINVAL, "apply_op_device: bad argument");
+    if (ctx->compact()) return fail(ctx, LGPU_EINVAL, "apply_op_device: mhd state vector only (device vectors are in the 16-wide layout)");
+    const cd* x = reinterpret_cast<const cd*>(x_dev);
+    cd* y = reinterpret_cast<cd*>(y_dev);
+    CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < repeat; ++r) dev_apply_op(ctx, x, y, refine_steps);
+    CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_per_application) *ms_per_application = static_cast<double>(ms) / repeat;
+    return LGPU_OK;
+  });
+}
+
 namespace {
 
 // hwork[0..2] of the last vec_dot2 -> host (synchronises the stream)

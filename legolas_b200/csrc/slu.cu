@@ -1254,15 +1254,17 @@ constexpr int NBF = 4;    // elimination steps per pass over the panel (divides 
 
 // Merge rows (2p, 2p+1) of a level: GE with partial pivoting over the 64 stacked rows of the
 // panel [T_2p ; S_2p+1]; block npairs (if present) carries the odd last row up unchanged.
+template <bool LOOKAHEAD>
 __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cd* W = reinterpret_cast<cd*>(smem_raw);          // [64][WLD]
-  cd* lcol = W + 64 * WLD;                          // [NBF][64] multipliers of the columns of a block of steps
+  cd* lcol = W + 64 * WLD;                          // [2][NBF][64] multipliers of the columns of a block of steps (two blocks in flight)
   // inverse of L11: lives in rows 32..63, columns 32..63 of W once the reduced rows stored there
   // have been written out (keeps the CTA at 100 KB of shared memory: two CTAs per SM)
   cd* X = W + 32 * WLD + 32;                        // X(i, c) at X[i * WLD + c]
-  int* prm = reinterpret_cast<int*>(lcol + NBF * 64);   // [64]
+  int* prm = reinterpret_cast<int*>(lcol + 2 * NBF * 64);   // [64]
   __shared__ double rscale[64];
+  __shared__ int pivs[2][NBF];                      // look-ahead: row swaps of a block not yet applied outside its panel
   const int tid = threadIdx.x;
   const int p = blockIdx.x;
   if (p == a.npairs) {   // odd row out
@@ -1359,6 +1361,148 @@ __global__ void __launch_bounds__(256) slu_merge_kernel(FactorArgs a) {
     }
     __syncwarp();
   };
+  // ---- look-ahead (default).  The serial part of a block keeps warp 0 busy for about as long as the rank-NBF update
+  // keeps all warps busy (ncu: 41 % of the kernel's warp samples were the other seven warps waiting at the barrier in
+  // front of the update), so the two now run side by side: while warps 1-7 apply block b to the columns right of the
+  // NEXT panel, warp 0 applies it to the next panel's NBF columns and factorises that panel.  Row swaps of a panel are
+  // applied inside the panel at once and everywhere else one iteration later, by whoever owns the column, in the same
+  // order; the pivot rows of a block are brought up to date column by column just before the rank-NBF update.  Every
+  // entry still sees the same operations in the same order: same pivots, bit-identical factors
+  // (LGPU_MERGE_LOOKAHEAD=0 runs the loop below; tests/test_gpu_paths.py compares).
+  if (LOOKAHEAD) {
+    // warp 0: factorise the panel of columns k .. k + NBF - 1 (rows >= k); swaps stay inside the panel
+    auto panel_factor = [&](int k, cd* lc, int* pv) {
+#pragma unroll
+      for (int j = 0; j < NBF; ++j) {
+        const int kj = k + j;
+        if (j > 0) {   // column k + j under the pivots k .. k + j - 1 of this block
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i >= kj) {
+              cd x = W[i * WLD + kj];
+#pragma unroll
+              for (int u = 0; u < j; ++u) cfms(x, lc[u * 64 + i], W[(k + u) * WLD + kj]);
+              W[i * WLD + kj] = x;
+            }
+          }
+          __syncwarp();
+        }
+        // pivot search (as pivot_and_swap)
+        const int i0 = lane, i1 = lane + 32;
+        double b0 = i0 >= kj ? abs2(W[i0 * WLD + kj]) : -1.0;
+        const double b1 = abs2(W[i1 * WLD + kj]);
+        int bi = i0;
+        if (b1 > b0) { b0 = b1; bi = i1; }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, b0, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+          if (ob > b0 || (ob == b0 && oi < bi)) { b0 = ob; bi = oi; }
+        }
+        const int pr = bi;
+        if (lane == 0 && !(b0 > 0.0)) {
+          const long long node = (static_cast<long long>(2 * p + 1) << a.level);
+          atomicCAS(a.info, 0, static_cast<int>(min(2 * node + 1, static_cast<long long>(a.n))));
+          W[pr * WLD + kj] = cd{2.2250738585072014e-308, 0.0};
+        }
+        __syncwarp();
+        if (lane == 0) pv[j] = pr;
+        if (pr != kj) {
+          if (lane < NBF) {   // inside the panel only
+            const int c = k + lane;
+            const cd t0 = W[kj * WLD + c];
+            W[kj * WLD + c] = W[pr * WLD + c];
+            W[pr * WLD + c] = t0;
+          }
+          if (lane == 0) {
+            const int t0 = prm[kj]; prm[kj] = prm[pr]; prm[pr] = t0;
+            for (int u = 0; u < j; ++u) { const cd t1 = lc[u * 64 + kj]; lc[u * 64 + kj] = lc[u * 64 + pr]; lc[u * 64 + pr] = t1; }
+          }
+        }
+        __syncwarp();
+        if (j > 0 && lane < NBF && k + lane > kj) {   // row k + j under the same pivots, panel columns
+          const int c = k + lane;
+          cd x = W[kj * WLD + c];
+#pragma unroll
+          for (int u = 0; u < j; ++u) cfms(x, lc[u * 64 + kj], W[(k + u) * WLD + c]);
+          W[kj * WLD + c] = x;
+        }
+        __syncwarp();
+        multipliers(kj, lc + j * 64);
+      }
+    };
+    // one thread, one column outside the panel of block k: its row swaps, then its pivot rows under the block's pivots
+    auto column_catch_up = [&](int k, const cd* lc, const int* pv, int c, bool update) {
+#pragma unroll
+      for (int j = 0; j < NBF; ++j) {
+        const int pr = pv[j];
+        if (pr != k + j) {
+          const cd t0 = W[(k + j) * WLD + c];
+          W[(k + j) * WLD + c] = W[pr * WLD + c];
+          W[pr * WLD + c] = t0;
+        }
+      }
+      if (update) {
+#pragma unroll
+        for (int j = 1; j < NBF; ++j) {
+          cd x = W[(k + j) * WLD + c];
+#pragma unroll
+          for (int u = 0; u < j; ++u) cfms(x, lc[u * 64 + k + j], W[(k + u) * WLD + c]);
+          W[(k + j) * WLD + c] = x;
+        }
+      }
+    };
+    // rank-NBF update of rows > kl of one column for the rows i = r0, r0 + rstep, ...
+    auto column_update = [&](int k, const cd* lc, int c, int r0, int rstep) {
+      const int kl = k + NBF - 1;
+      cd wk[NBF];
+#pragma unroll
+      for (int u = 0; u < NBF; ++u) wk[u] = W[(k + u) * WLD + c];
+      for (int i = r0; i < 64; i += rstep) {
+        if (i > kl) {
+          cd x = W[i * WLD + c];
+#pragma unroll
+          for (int u = 0; u < NBF; ++u) cfms(x, lc[u * 64 + i], wk[u]);
+          W[i * WLD + c] = x;
+        }
+      }
+    };
+    if (tid < 32) panel_factor(0, lcol, pivs[0]);
+    __syncthreads();
+    for (int b = 0; b < SB / NBF; ++b) {
+      const int k = b * NBF, kl = k + NBF - 1;
+      const cd* lc = lcol + (b & 1) * NBF * 64;
+      const int* pv = pivs[b & 1];
+      const bool last = b == SB / NBF - 1;
+      if (!last && tid < 32) {
+        // warp 0: block b on the next panel's columns, then that panel
+        if (lane < NBF) column_catch_up(k, lc, pv, kl + 1 + lane, true);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NBF; ++q) column_update(k, lc, kl + 1 + q, lane, 32);
+        __syncwarp();
+        panel_factor(k + NBF, lcol + ((b + 1) & 1) * NBF * 64, pivs[(b + 1) & 1]);
+      } else {
+        // the other warps (all of them for the last block): columns left of the block get its swaps, columns right
+        // of the next panel the swaps, the pivot-row update and the rank-NBF update
+        const int team0 = last ? 0 : 32, nteam = 256 - team0, tt = tid - team0;
+        const int cfirst = last ? kl + 1 : kl + 1 + NBF;           // first column right of the work of warp 0
+        for (int c = tt; c < 96; c += nteam) {
+          if (c < k) column_catch_up(k, lc, pv, c, false);
+          else if (c >= cfirst) column_catch_up(k, lc, pv, c, true);
+        }
+        if (last) __syncthreads(); else asm volatile("bar.sync 2, 224;" ::: "memory");
+        const int nrg = nteam >> 5, myrg = tt >> 5;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const int c = lane + 32 * cc;
+          if (c >= cfirst) column_update(k, lc, c, myrg, nrg);
+        }
+      }
+      __syncthreads();
+    }
+  } else
   for (int k = 0; k < SB; k += NBF) {
     if (tid < 32) {
 #pragma unroll
@@ -1726,7 +1870,7 @@ RingShape bwd_shape(const StageArgs& a, bool top) {
   return RingShape{ns, nu, bytes(ns, nu)};
 }
 
-constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + NBF * 64) + sizeof(int) * 64;   // 101 KiB: two CTAs per SM
+constexpr size_t MERGE_SMEM = sizeof(cd) * (64 * WLD + 2 * NBF * 64) + sizeof(int) * 64;   // 105 KiB: two CTAs per SM
 constexpr size_t TOPF_SMEM = sizeof(cd) * (2 * 64 * TLD + 64) + sizeof(int) * 64;
 
 void configure_kernels() {
@@ -1738,7 +1882,8 @@ void configure_kernels() {
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_fused_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CUDA_CHECK(cudaFuncSetAttribute(slu_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(slu_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CUDA_CHECK(cudaFuncSetAttribute(slu_top_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   });
 }
@@ -1772,7 +1917,9 @@ void slu_factorize(const SluPlan& plan, const SluDevice& d, cd sigma, cudaStream
     a.m = lv.m;
     a.npairs = lv.npairs;
     a.level = l;
-    slu_merge_kernel<<<lv.npairs + (lv.m & 1), 256, MERGE_SMEM, stream>>>(a);
+    static const bool lookahead = [] { const char* e = std::getenv("LGPU_MERGE_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+    if (lookahead) slu_merge_kernel<true><<<lv.npairs + (lv.m & 1), 256, MERGE_SMEM, stream>>>(a);
+    else slu_merge_kernel<false><<<lv.npairs + (lv.m & 1), 256, MERGE_SMEM, stream>>>(a);
     log->launches += 1;
   }
   a.src = rows_of(nl);

@@ -34,6 +34,11 @@ for name, G, sigma, nev, ncv in (("magnetothermal_instabilities", 1501, 0.02 + 0
     omega, vr, cfg, stats = lb.solve_evp(mats, s)
     order = np.argsort(np.abs(omega - sigma))
     out[name] = {"nconv": stats["nconv"], "re": omega.real[order].tolist(), "im": omega.imag[order].tolist()}
+    # fingerprint of the factorisation + solve kernels: the bits of one solve with the factors of the last shift
+    import hashlib
+    rhs = np.cos(np.arange(mats.ctx.dim) * 0.37) + 1j * np.sin(np.arange(mats.ctx.dim) * 0.11)
+    mats.ctx.factorize(sigma)
+    out[name]["solve_sha"] = hashlib.sha256(np.ascontiguousarray(mats.ctx.solve(rhs)).tobytes()).hexdigest()
 print("RESULT " + json.dumps(out))
 """
 
@@ -62,6 +67,7 @@ def default_result():
     {"LGPU_GEMM_MMA": "0", "LGPU_GEMM_ROWS": "0"},   # shared-memory tiled restart GEMM
     {"LGPU_SLU_UPPER": "0"},                     # upper solve stages streamed through rings (cooperative launch)
     {"LGPU_BX_FUSE": "0"},                       # separate launch for the B x product
+    {"LGPU_MERGE_LOOKAHEAD": "0"},               # factorisation without look-ahead (panel, then update)
     {"LGPU_SLU_MU0": "3", "LGPU_SLU_MU1": "3", "LGPU_SLU_TOP": "32"},  # another stage tree
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
 def test_variant_matches_default(default_result, env_extra):
@@ -76,3 +82,8 @@ def test_variant_matches_default(default_result, env_extra):
         # same algorithm, different summation orders: agreement at the level the eigenvalues are
         # determined by the pencil (1e-8 relative is the parity bar of the path)
         assert np.all(np.abs(a - b) <= 1e-8 * np.abs(b)), (name, np.abs(a - b).max())
+        # variants that leave the factorisation / solve kernels alone, or claim the same operations per entry in the same
+        # order (look-ahead), must reproduce the solve bit for bit
+        if set(env_extra) <= {"LGPU_MERGE_LOOKAHEAD", "LGPU_GEMM_MMA", "LGPU_GEMM_ROWS", "LGPU_CGS2_FUSED", "LGPU_CGS2_EXACT",
+                              "LGPU_B_ELL", "LGPU_BX_FUSE"}:
+            assert got[name]["solve_sha"] == ref["solve_sha"], name
