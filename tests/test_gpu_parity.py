@@ -232,6 +232,42 @@ def test_adiabatic_shift_invert_golden_baseline(ctx, golden):
         assert np.min(np.abs(omega - w)) <= 1e-10 * abs(w)
 
 
+@pytest.mark.parametrize("sigma", [5.0, 10.0, 15.0, 20.0, 25.0])
+def test_config1_shift_scan_against_qr_invert_spectrum(ctx, golden, sigma):
+    """BASELINE config 1 (adiabatic_homo, G = 51): device shift-invert at sigma in {5, 10, 15, 20, 25} (SURVEY section 8(d),
+    item 1) against the QR-invert FULL spectrum - the oracle's (smod_qr_invert.f08:46-135) and the one the reference stores
+    (BASE_uni_adiab_QR_k2_0_k3_pi.dat): the six values returned are the six eigenvalues of the spectrum nearest the shift."""
+    g = golden("uni_adiab_QR")
+    s, grid, fields = heq.adiabatic_homo(51)
+    s.gauss_nodes, s.gauss_weights = asm.LEGACY_GAUSS_NODES, asm.LEGACY_GAUSS_WEIGHTS
+    grid = heq.Grid(s, 0.0, 1.0, nodes=asm.LEGACY_GAUSS_NODES)
+    s.solvers = lb.SolverSettings(solver="arnoldi", arpack_mode="shift-invert", number_of_eigenvalues=6, sigma=complex(sigma))
+    mats = lb.build_matrices(s, grid.base_grid, grid.gaussian_grid, fields, ctx=ctx)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        omega, _, _, stats = lb.solve_evp(mats, s)
+    so, go, xgo, fo = oeq.adiabatic_homo_eq(gridpts=51, nodes=asm.LEGACY_GAUSS_NODES)
+    so.gauss_nodes, so.gauss_weights = asm.LEGACY_GAUSS_NODES, asm.LEGACY_GAUSS_WEIGHTS
+    A, B = asm.build_matrices(so, go, xgo, fo)
+    # the reference-equivalent shift-invert run: at sigma = 5 and 10 the six nearest eigenvalues are members of the
+    # degenerate cluster omega = k3 = pi (hundreds of copies), of which ARPACK converges 2 resp. 4 before maxiter - the
+    # device must stop with the same count; at 15, 20, 25 all six are simple and converge
+    om_o, _, st_o = osolvers.shift_invert(A.to_band(), B.to_band(), 31, 31, complex(sigma), 6, return_stats=True)
+    assert stats["nconv"] == st_o["nconv"] == (6 if sigma >= 15 else st_o["nconv"])
+    got = omega[:stats["nconv"]]
+    for w in got:
+        assert np.min(np.abs(om_o - w)) <= 1e-8 * abs(w), (sigma, w)
+    for spectrum in (osolvers.qr_invert(A.to_dense(), B.to_dense()), g["eigenvalues"]):
+        spectrum = spectrum[np.isfinite(spectrum) & (np.abs(spectrum) < 1e10)]
+        for w in got:                                       # every returned value is an eigenvalue of the full spectrum
+            assert np.min(np.abs(spectrum - w)) <= 1e-8 * abs(w), (sigma, w)
+        if stats["nconv"] == 6:                             # ... and they are the six nearest the shift
+            nearest = spectrum[np.argsort(np.abs(spectrum - sigma))[:6]]
+            for w in nearest:
+                assert np.min(np.abs(got - w)) <= 1e-8 * abs(w), (sigma, w)
+
+
 # ---- tests/unit_tests/mod_test_solvers_arpack_shift_invert.pf (10 x 10 pencil, 6 shifts)
 @pytest.mark.parametrize("sigma,idxs", [
     (0.0 + 0.0j, [1, 2, 3, 5]), (1.0 + 0.0j, [3, 5, 6, 8]), (0.5j, [3, 4, 5, 6]),
