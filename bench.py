@@ -541,7 +541,8 @@ def run_sharded_sections(args, rank, world, local_rank, device):
                    "check": check}
     # ---- config 5: wavenumber sweep
     units = wl.sweep_units(args.sweep_units)
-    workers = max(1, args.sweep_workers)
+    # units in flight per GPU, bounded by the host cores a rank can count on (every worker is a host thread)
+    workers = max(1, min(args.sweep_workers, (os.cpu_count() or 8) // max(world, 1)))
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     solvers = [wl.SweepSolver(device=local_rank, sm_limit=sms // workers if workers > 1 else 0) for _ in range(workers)]
     _, cost_table, _ = timed_pass(units, list(range(len(units))), solvers, wl.SWEEP_NEV)

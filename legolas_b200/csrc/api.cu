@@ -131,6 +131,7 @@ struct lgpu_ctx {
 
   LaunchLog log;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_block = nullptr;   // blocking-sync event of stream_sync()
   double t_assemble = 0, t_factor = 0, t_iter = 0, t_extract = 0;
 
   bool assembled() const { return have[0] && have[1]; }
@@ -142,6 +143,20 @@ struct lgpu_ctx {
     return d;
   }
 };
+
+// Wait for the context's stream.  A context that shares its GPU (lgpu_set_sm_limit > 0: several host threads drive
+// several contexts) sleeps on a blocking event instead of spinning, so that the waiting threads of a sweep do not
+// compete for the host cores with the ones that have launches to issue.
+inline cudaError_t stream_sync(lgpu_ctx* c) {
+  if (c->sm_limit <= 0) return cudaStreamSynchronize(c->stream);
+  if (!c->ev_block) {
+    const cudaError_t e = cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  const cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(c->ev_block);
+}
 
 namespace {
 
@@ -382,7 +397,7 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
   c->d_items.ensure(items.size());
   CUDA_CHECK(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(PairItem),
                              cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));   // host vectors go out of scope below
+  CUDA_CHECK(stream_sync(c));   // host vectors go out of scope below
   DevicePlan de{pe.nslots(), static_cast<int32_t>(pe.items.size()), c->d_plan_i32.p + o_sb_e,
                 c->d_plan_i32.p + o_t_e, c->d_items.p};
   DevicePlan dn{pn.nslots(), static_cast<int32_t>(pn.items.size()), c->d_plan_i32.p + o_sb_n,
@@ -451,7 +466,7 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
     CUDA_CHECK(cudaMemcpyAsync(bmeta, c->bell_width.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   }
   CUDA_CHECK(cudaMemcpyAsync(&info, c->d_info.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK(stream_sync(c));
   c->bell_w = bmeta[0];
   c->bell_real = bmeta[1] == 0;
   float ms = 0.f;
@@ -553,7 +568,7 @@ class CudaKrylovOps final : public KrylovOps {
                                c_->stream));
     CUDA_CHECK(cudaMemcpyAsync(c_->h_scal.p, c_->kscal.p, sizeof(double), cudaMemcpyDeviceToHost,
                                c_->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c_->stream));
+    CUDA_CHECK(stream_sync(c_));
     for (int j = k; j < m; ++j) {
       for (int i = 0; i <= j; ++i) {
         const cd v = c_->h_stage.p[static_cast<size_t>(j) * ncv_ + i];
@@ -645,7 +660,7 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   Iram iram;
   const double t0 = now_ms();
   IramResult res = iram.run(ops, ic);
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK(stream_sync(c));
   const double t1 = now_ms();
   const double nan = std::numeric_limits<double>::quiet_NaN();
   for (int k = 0; k < nev; ++k) {
@@ -666,10 +681,10 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
       if (all > got)
         CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<cd*>(vr_out) + got, 0, (all - got) * sizeof(cd),
                                    c->stream));
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(stream_sync(c));
     } else {
       if (res.nconv > 0) vec_out(c, c->Z.p, vr_out, false, res.nconv);
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(stream_sync(c));
       if (all > got) std::memset(vr_out + 2 * got, 0, (all - got) * sizeof(cd));
     }
   }
@@ -723,9 +738,10 @@ int lgpu_create(lgpu_ctx** out, int32_t device, int32_t log_level) {
 int lgpu_destroy(lgpu_ctx* ctx) {
   if (!ctx) return LGPU_EINVAL;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  stream_sync(ctx);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   cudaStream_t own = ctx->own_stream ? ctx->stream : nullptr;
   delete ctx;
   if (own) cudaStreamDestroy(own);
@@ -736,7 +752,7 @@ const char* lgpu_last_error(const lgpu_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int lgpu_set_stream(lgpu_ctx* ctx, void* cuda_stream) {
   return guarded(ctx, [&] {
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     if (ctx->own_stream) {
       if (cuda_stream == nullptr) return LGPU_OK;
       cudaStreamDestroy(ctx->stream);
@@ -761,7 +777,7 @@ int lgpu_set_sm_limit(lgpu_ctx* ctx, int32_t max_sms) {
 
 int lgpu_synchronize(lgpu_ctx* ctx) {
   return guarded(ctx, [&] {
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     return LGPU_OK;
   });
 }
@@ -817,7 +833,7 @@ int lgpu_export_blocks(lgpu_ctx* ctx, int32_t which, double* blocks_ri) {
       std::vector<cd> blocks(cnt);
       CUDA_CHECK(cudaMemcpyAsync(blocks.data(), which ? ctx->B.p : ctx->A.p, cnt * sizeof(cd),
                                  cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      CUDA_CHECK(stream_sync(ctx));
       const int d = ctx->dsub;
       for (size_t t = 0; t < static_cast<size_t>(ctx->G) * 3; ++t)
         for (int j = 0; j < d; ++j)
@@ -831,7 +847,7 @@ int lgpu_export_blocks(lgpu_ctx* ctx, int32_t which, double* blocks_ri) {
     }
     CUDA_CHECK(cudaMemcpyAsync(blocks_ri, which ? ctx->B.p : ctx->A.p, cnt * sizeof(cd),
                                cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     return LGPU_OK;
   });
 }
@@ -851,7 +867,7 @@ int lgpu_export_coo(lgpu_ctx* ctx, int32_t which, int64_t* nnz, int32_t* rows, i
                                cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(nat.data(), ctx->natmasks.p, nat.size() * sizeof(uint32_t),
                                cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     auto bit = [](const uint32_t* w, int idx) { return (w[idx >> 5] >> (idx & 31)) & 1u; };
     int inv[BLK];   // device row within a block -> row in the reference's numbering
     for (int i = 0; i < BLK; ++i) inv[i] = 0;
@@ -964,7 +980,7 @@ int lgpu_solve(lgpu_ctx* ctx, const double* rhs_ri, double* x_ri, int32_t refine
     vec_in(ctx, rhs_ri, false, ctx->vx.p);
     dev_solve(ctx, ctx->vx.p, ctx->vy.p, refine_steps);
     vec_out(ctx, ctx->vy.p, x_ri, false);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     return LGPU_OK;
   });
 }
@@ -979,7 +995,7 @@ int lgpu_matvec(lgpu_ctx* ctx, int32_t which, const double* x_ri, double* y_ri) 
                  cd{which == 1 ? 1.0 : 0.0, 0.0}, ctx->vx.p, nullptr, ctx->vy.p, ctx->stream,
                  &ctx->log);
     vec_out(ctx, ctx->vy.p, y_ri, false);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     return LGPU_OK;
   });
 }
@@ -991,7 +1007,7 @@ int lgpu_apply_op(lgpu_ctx* ctx, const double* x_ri, double* y_ri, int32_t refin
     vec_in(ctx, x_ri, false, ctx->vx.p);
     dev_apply_op(ctx, ctx->vx.p, ctx->vy.p, refine_steps);
     vec_out(ctx, ctx->vy.p, y_ri, false);
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     return LGPU_OK;
   });
 }
@@ -1021,7 +1037,7 @@ namespace {
 void fetch_dots(lgpu_ctx* c, cd out[3]) {
   c->h_stage.ensure(4);
   CUDA_CHECK(cudaMemcpyAsync(c->h_stage.p, c->khwork.p, 3 * sizeof(cd), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK(stream_sync(c));
   for (int k = 0; k < 3; ++k) out[k] = c->h_stage.p[k];
 }
 
@@ -1087,7 +1103,7 @@ int lgpu_eigenfunctions(lgpu_ctx* ctx, const double* vr_ri, int32_t nsel, const 
     for (int q = 0; q < ctx->dsub / 2; ++q)
       CUDA_CHECK(cudaMemcpyAsync(out_ri + 2 * slab * q, ctx->ef_out.p + slab * (ctx->cmap[2 * q] / 2), sizeof(cd) * slab,
                                  cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     return LGPU_OK;
   });
 }
@@ -1120,7 +1136,7 @@ int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int3
     {
       std::vector<cd> ones(static_cast<size_t>(c->Nc()), cd{1.0, 0.0});
       vec_in(c, ones.data(), false, x);
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(stream_sync(c));
     }
     slu_solve(c->splan, c->sdev(), x, x, c->stream, &c->log);
     normalise(x);
@@ -1147,7 +1163,7 @@ int lgpu_inverse_iteration(lgpu_ctx* ctx, double sigma_re, double sigma_im, int3
     if (vr_ri) {
       std::vector<cd> h(static_cast<size_t>(c->Nc()));
       vec_out(c, x, h.data(), false);
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(stream_sync(c));
       // make the largest coefficient real (first maximum, as idamax)
       size_t im = 0;
       double best = -1.0;
@@ -1247,7 +1263,7 @@ int lgpu_counters(lgpu_ctx* ctx, int64_t* kernel_launches, int32_t reset) {
 
 int lgpu_set_profiling(lgpu_ctx* ctx, int32_t enable) {
   return guarded(ctx, [&] {
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     ctx->log.stream = ctx->stream;
     ctx->log.reset();
     ctx->log.profiling = enable != 0;
@@ -1258,7 +1274,7 @@ int lgpu_set_profiling(lgpu_ctx* ctx, int32_t enable) {
 int lgpu_profile_read(lgpu_ctx* ctx, double* ms, int64_t* counts, double* algo_bytes,
                       int32_t nkinds, int32_t reset) {
   return guarded(ctx, [&] {
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(stream_sync(ctx));
     ctx->log.collect();
     for (int k = 0; k < nkinds && k < LK_COUNT; ++k) {
       if (ms) ms[k] = ctx->log.ms[k];

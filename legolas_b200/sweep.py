@@ -47,30 +47,45 @@ class WorkQueue:
 
     With torch.distributed initialised the counter lives in the default store (TCPStore on rank 0;
     ``store.add`` is atomic); otherwise it is a local counter.  Every rank must construct its queues
-    in the same order (the key is numbered per process)."""
+    in the same order (the key is numbered per process).  A draw takes a CHUNK of consecutive positions
+    per store round trip - guided self-scheduling: about 1 / (4 x drawers) of what is left, at least one -
+    so that short units do not pay a round trip each while the tail of the queue is still handed out one
+    by one; the positions of a chunk are served to the threads of the rank in order."""
 
-    def __init__(self, n: int, group=None):
+    def __init__(self, n: int, group=None, drawers: int = 1):
         self.n = int(n)
         self._lock = threading.Lock()
         self._local = 0
         self._store = None
+        self._buf: List[int] = []
+        self._seen = 0          # highest position this rank has seen handed out (estimate of the queue head)
+        self._drawers = max(1, int(drawers))
         dist = _dist()
         if dist is not None and dist.get_world_size(group) > 1:
             from torch.distributed import distributed_c10d as c10d
 
             self._store = c10d._get_default_store()
             self._key = f"legolas_b200/queue/{next(_QUEUE_SEQ)}"
+            self._drawers *= dist.get_world_size(group)
         else:
             next(_QUEUE_SEQ)
 
     def next(self) -> Optional[int]:
         with self._lock:
-            if self._store is not None:
-                pos = int(self._store.add(self._key, 1)) - 1
-            else:
-                pos = self._local
-                self._local += 1
-        return pos if pos < self.n else None
+            if not self._buf:
+                if self._seen >= self.n:
+                    return None
+                chunk = max(1, (self.n - self._seen) // (4 * self._drawers))
+                if self._store is not None:
+                    end = int(self._store.add(self._key, chunk))
+                else:
+                    self._local += chunk
+                    end = self._local
+                self._seen = end
+                self._buf = [p for p in range(end - chunk, end) if p < self.n]
+                if not self._buf:
+                    return None
+            return self._buf.pop(0)
 
     def __iter__(self):
         while True:
@@ -136,7 +151,7 @@ def run_queue(units: Sequence, make_solver: Callable[[int], Callable], nev: int,
     order = list(range(len(units))) if order is None else list(order)
     if sorted(order) != list(range(len(units))):
         raise ValueError("order must be a permutation of the unit indices")
-    queue = WorkQueue(len(order), group=group)
+    queue = WorkQueue(len(order), group=group, drawers=len(solvers) if solvers is not None else max(1, workers))
     table = np.full((len(units), nev), np.nan + 1j * np.nan, dtype=np.complex128)
     mine: List[int] = []
     errors: List[BaseException] = []
