@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <atomic>
 #include <condition_variable>
+#include <thread>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -144,11 +146,21 @@ struct lgpu_ctx {
   }
 };
 
-// Wait for the context's stream.  A context that shares its GPU (lgpu_set_sm_limit > 0: several host threads drive
-// several contexts) sleeps on a blocking event instead of spinning, so that the waiting threads of a sweep do not
-// compete for the host cores with the ones that have launches to issue.
+// Wait for the context's stream.  Contexts that share their GPU (lgpu_set_sm_limit > 0: several host threads drive
+// several contexts per process) sleep on a blocking event instead of spinning when the host is short of cores -
+// waiting threads of all ranks of the node (LOCAL_WORLD_SIZE processes x sharing contexts each) x 2 > hardware threads -
+// so that they do not take the cores from the threads that have launches to issue; with cores to spare spinning is
+// faster (measured, 256-unit sweep, three contexts, 32 cores: 0.66 s spinning, 0.78 s blocking).
+inline std::atomic<int>& sharing_contexts() { static std::atomic<int> n{0}; return n; }
+inline bool blocking_waits() {
+  if (const char* e = std::getenv("LGPU_BLOCKING_SYNC")) return e[0] != '0';
+  int ranks = 1;
+  if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, std::atoi(e));
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  return 2u * static_cast<unsigned>(ranks * std::max(1, sharing_contexts().load())) > hw;
+}
 inline cudaError_t stream_sync(lgpu_ctx* c) {
-  if (c->sm_limit <= 0) return cudaStreamSynchronize(c->stream);
+  if (c->sm_limit <= 0 || !blocking_waits()) return cudaStreamSynchronize(c->stream);
   if (!c->ev_block) {
     const cudaError_t e = cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
@@ -742,6 +754,7 @@ int lgpu_destroy(lgpu_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
+  if (ctx->sm_limit > 0) sharing_contexts() -= 1;
   cudaStream_t own = ctx->own_stream ? ctx->stream : nullptr;
   delete ctx;
   if (own) cudaStreamDestroy(own);
@@ -770,6 +783,7 @@ int lgpu_set_stream(lgpu_ctx* ctx, void* cuda_stream) {
 
 int lgpu_set_sm_limit(lgpu_ctx* ctx, int32_t max_sms) {
   if (!ctx || max_sms < 0) return LGPU_EINVAL;
+  if ((ctx->sm_limit > 0) != (max_sms > 0)) sharing_contexts() += max_sms > 0 ? 1 : -1;
   ctx->sm_limit = max_sms;
   ctx->demand_G = -1;
   return LGPU_OK;
