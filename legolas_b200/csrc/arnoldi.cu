@@ -212,6 +212,24 @@ krylov_pass_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, int nstag
 // producer warp keeps streaming the next pass's tiles while the consumers wait (V does not
 // change during the step).  The CTA's rows of w stay in shared memory from the first pass to the
 // normalisation.  Saves three launches and their fill/drain per step and two passes over w.
+// Optional timeline of the fused step (-DLGPU_TRACE, scripts/cgs_trace.py): thread 0 of every CTA stores %globaltimer
+// at phase boundaries.  Never compiled into the product library.
+#ifdef LGPU_TRACE
+constexpr int CTRACE_SLOTS = 16, CTRACE_CTAS = 160;
+__device__ unsigned long long g_cgs_trace[CTRACE_CTAS * CTRACE_SLOTS];
+__device__ __forceinline__ void cgs_trace_mark(int slot) {
+  if (threadIdx.x == 0 && blockIdx.x < CTRACE_CTAS) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cgs_trace[blockIdx.x * CTRACE_SLOTS + slot] = t;
+  }
+  __syncwarp();
+}
+#define CGS_MARK(s) cgs_trace_mark(s)
+#else
+#define CGS_MARK(s)
+#endif
+
 struct CgsArgs {
   BasisLayout L;
   cd* V;
@@ -317,6 +335,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   const int t0 = static_cast<int>(static_cast<long long>(blockIdx.x) * L.ntiles / gridDim.x);
   const int t1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * L.ntiles / gridDim.x);
   const int nt = t1 - t0;
+  CGS_MARK(0);
   if (tid == 0) {
     for (int i = 0; i < nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -394,6 +413,10 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   // in pass 2 against 1.2 k cycles per tile of arrival); two independent chains share one barrier.  Same operations
   // per entry in the same order as one tile at a time.
   cd v2[NJ];
+  // The four partial sums of row r come from warps (r / 32) + 2 q: rows 0 - 31 and rows 32 - 63 never exchange
+  // anything, so each half of the tile has a barrier of its own (128 threads); every scheduler holds one warp of each
+  // half, and a half that waits for its exchange leaves the issue slots to the other one.
+  auto half_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 1)) : "memory"); };
   auto correct_pair = [&](int ia, int ib, cd& wa, cd& wb) {
     cd pa0{0.0, 0.0}, pa1{0.0, 0.0}, pb0{0.0, 0.0}, pb1{0.0, 0.0};
     const cd* hq = hs + q * NJ;
@@ -408,7 +431,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     pp[q * PASS_T + r] = pa0 + pa1;
     pp[(PASS_GROUPS + q) * PASS_T + r] = pb0 + pb1;
     const cd wolda = wkeep[ia * PASS_T + r], woldb = wkeep[ib * PASS_T + r];
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    half_sync();
     const cd* pb = pp + PASS_GROUPS * PASS_T;
     wa = wolda - ((pp[r] + pp[PASS_T + r]) + (pp[2 * PASS_T + r] + pp[3 * PASS_T + r]));
     wb = woldb - ((pb[r] + pb[PASS_T + r]) + (pb[2 * PASS_T + r] + pb[3 * PASS_T + r]));
@@ -436,7 +459,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     flip ^= 1;
     pp[q * PASS_T + r] = p0 + p1;
     const cd wold = wkeep[i * PASS_T + r];
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    half_sync();
     return wold - ((pp[r] + pp[PASS_T + r]) + (pp[2 * PASS_T + r] + pp[3 * PASS_T + r]));
   };
   auto publish_dots = [&](cd* dst) {   // rows -> one value per (CTA, column)
@@ -470,14 +493,21 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   for (int i = 0; i < nt; ++i) {
     cd wi{0.0, 0.0};
     load_tile(1, i, true, wi);
+#ifdef LGPU_TRACE
+    if (i == 0) CGS_MARK(1);
+#endif
     if (q == 0) wkeep[i * PASS_T + r] = wi;
 #pragma unroll
     for (int j = 0; j < NJ; ++j)
       if (EXACT || j < cpg) cfmac(acc[j], v[j], wi);
   }
+  CGS_MARK(2);
   publish_dots(partial1);
+  CGS_MARK(3);
   cgs_grid_barrier(a.gbar, a.bar_base + gridDim.x);
+  CGS_MARK(4);
   cgs_sum_partials(partial1, ncols, hs, part, tid);
+  CGS_MARK(5);
   if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = hs[c];
 
   // ---- pass 2: w -= V h ; s = V^H w ; || w ||^2
@@ -514,24 +544,31 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     for (int j = 0; j < NJ; ++j)
       if (EXACT || j < cpg) cfmac(acc[j], v[j], wi);
   }
+  CGS_MARK(6);
   publish_dots(partial2);
   nrm = warp_sum(nrm);
   if (lane == 0) red[warp] = nrm;
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (tid == 0) partial2[static_cast<size_t>(blockIdx.x) * PSTRIDE + KRYLOV_MAXCOL] = cd{red[0] + red[1], 0.0};
+  CGS_MARK(7);
   cgs_grid_barrier(a.gbar, a.bar_base + 2ull * gridDim.x);
+  CGS_MARK(8);
+  // the per-CTA squared norms travel with the partials (the loads are issued first and are in flight during the
+  // summation of the partials: one L2 round trip for both)
+  double x[CGS_MAX_GRID / 32];
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < CGS_MAX_GRID / 32; ++k) {
+      const unsigned int b = lane + 32 * k;
+      x[k] = b < gridDim.x ? ldcg_cd(partial2 + static_cast<size_t>(b) * PSTRIDE + KRYLOV_MAXCOL).x : 0.0;
+    }
+  }
   cgs_sum_partials(partial2, ncols, hs, part, tid);
   if (blockIdx.x == 0) for (int c = tid; c < ncols; c += 256) a.Hcol[c] = a.Hcol[c] + hs[c];
   // The norm of the final residual without a third device-wide round: the basis is orthonormal,
   // so || w - V s ||^2 = || w ||^2 - || s ||^2, and after the first correction || s || is at
   // rounding level of || w || (no cancellation).  Every CTA evaluates it in the same order.
   if (warp == 0) {
-    double x[CGS_MAX_GRID / 32];
-#pragma unroll
-    for (int k = 0; k < CGS_MAX_GRID / 32; ++k) {
-      const unsigned int b = lane + 32 * k;
-      x[k] = b < gridDim.x ? ldcg_cd(partial2 + static_cast<size_t>(b) * PSTRIDE + KRYLOV_MAXCOL).x : 0.0;
-    }
     double wn2 = 0.0;
 #pragma unroll
     for (int k = 0; k < CGS_MAX_GRID / 32; ++k) wn2 += x[k];
@@ -548,6 +585,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     if (a.newcol >= 0 && a.hsub) *a.hsub = cd{rnorm, 0.0};
   }
 
+  CGS_MARK(9);
   // ---- pass 3: w -= V s, and the next basis vector V(:, newcol) = vplain = w / ||w|| on the way
   const double inv = 1.0 / rnorm;
   auto emit = [&](int i, cd wi) {
@@ -580,6 +618,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     wi = correct(i);
     emit(i, wi);
   }
+  CGS_MARK(10);
 }
 
 __device__ __forceinline__ size_t basis_off(const BasisLayout& L, int i, int c) {
@@ -828,6 +867,12 @@ vec_axpby_kernel(int n, cd a, cd* __restrict__ r, cd b, const cd* __restrict__ v
 }
 
 }  // namespace
+
+#ifdef LGPU_TRACE
+extern "C" int lgpu_debug_cgs_trace(unsigned long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, g_cgs_trace, sizeof(unsigned long long) * CTRACE_CTAS * CTRACE_SLOTS));
+}
+#endif
 
 BasisLayout make_basis_layout(int n, int ncv) {
   BasisLayout L{};
