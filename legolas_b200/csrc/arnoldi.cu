@@ -364,6 +364,11 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         bulk_g2s_hint(sb, a.V + static_cast<size_t>(t) * L.ncv * PASS_T, vbytes, &full[sg], keep_policy);
         if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[sg]);
       };
+      // Programmatic dependent launch (krylov_cgs2_step): this CTA may be running while the kernel that produces w
+      // is still at work; nothing is read before that kernel has completed.  (The basis tiles could be requested
+      // earlier only with a completion protocol of their own: the newest column is written by the previous step's
+      // launch, and an early start is ordered after the START of the kernels in between, not after their end.)
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int i = 0; i < nt; ++i) fill(i, cgs_fill_number(1, i, nt, sd), true);
       for (int i = nt - S - 1; i >= 0; --i) fill(i, cgs_fill_number(2, i, nt, sd), false);
       for (int i = S; i < nt; ++i) fill(i, cgs_fill_number(3, i, nt, sd), false);
@@ -371,6 +376,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     return;
   }
   // ---- consumers: 64 rows x 4 column groups
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may stage its static data early
+  asm volatile("griddepcontrol.wait;" ::: "memory");                // nothing below may precede the kernel before this one
   const int cpg = EXACT ? CPG : (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
   const int r = tid & (PASS_T - 1), q = tid >> 6;
   if (EXACT) {   // coefficients of the padding columns stay zero for the whole step
@@ -952,12 +959,36 @@ static size_t cgs2_smem(int ncols, int nstages, int tiles_max) {
 }
 
 template <int CPG>
-static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t stream) {
+static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t stream, bool pdl) {
   static PerDeviceOnce once;
   once.run([] {
     CUDA_CHECK(cudaFuncSetAttribute(krylov_cgs2_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(CGS2_SMEM_MAX)));
   });
+  // Cooperative (all CTAs co-resident: they meet at device-wide barriers) and, for a context that has the GPU to
+  // itself, programmatic: the CTAs start while the last solve kernel is still running, initialise their barriers and
+  // stream their first basis tiles, and block in griddepcontrol.wait until w is complete.  A context that shares the
+  // GPU (SM cap set) keeps the plain launch: its admission ticket counts the solve kernels OR this grid, not both.
+  static const bool pdl_env = [] { const char* e = std::getenv("LGPU_PDL"); return !(e && e[0] == '0'); }();
+  static bool pdl_ok = true;   // cleared if the driver rejects the attribute pair
+  if (pdl && pdl_env && pdl_ok) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(PASS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    const cudaError_t rc = cudaLaunchKernelEx(&cfg, krylov_cgs2_kernel<CPG>, a);
+    if (rc == cudaSuccess) return;
+    (void)cudaGetLastError();
+    pdl_ok = false;
+  }
   void* args[] = {const_cast<CgsArgs*>(&a)};
   CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(krylov_cgs2_kernel<CPG>), dim3(grid), dim3(PASS_THREADS),
                                          args, smem, stream));
@@ -992,14 +1023,15 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   const size_t smem = cgs2_smem(ncopy, nstages, tiles_max);
   // one orthogonalisation at basis size j = two passes, 2 (j + 2) 256 G bytes
   log->begin(LK_CGS2, 16.0 * L.n * (2.0 * ncols + 4.0));
+  const bool pdl = work.grid_cap <= 0;
   switch (exact ? cpg : 0) {
-    case 5: launch_cgs2<5>(a, grid, smem, stream); break;
-    case 6: launch_cgs2<6>(a, grid, smem, stream); break;
-    case 7: launch_cgs2<7>(a, grid, smem, stream); break;
-    case 8: launch_cgs2<8>(a, grid, smem, stream); break;
-    case 9: launch_cgs2<9>(a, grid, smem, stream); break;
-    case 10: launch_cgs2<10>(a, grid, smem, stream); break;
-    default: launch_cgs2<0>(a, grid, smem, stream); break;
+    case 5: launch_cgs2<5>(a, grid, smem, stream, pdl); break;
+    case 6: launch_cgs2<6>(a, grid, smem, stream, pdl); break;
+    case 7: launch_cgs2<7>(a, grid, smem, stream, pdl); break;
+    case 8: launch_cgs2<8>(a, grid, smem, stream, pdl); break;
+    case 9: launch_cgs2<9>(a, grid, smem, stream, pdl); break;
+    case 10: launch_cgs2<10>(a, grid, smem, stream, pdl); break;
+    default: launch_cgs2<0>(a, grid, smem, stream, pdl); break;
   }
   log->end();
   log->launches += 1;
