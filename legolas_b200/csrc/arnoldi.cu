@@ -376,8 +376,10 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     return;
   }
   // ---- consumers: 64 rows x 4 column groups
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may stage its static data early
-  asm volatile("griddepcontrol.wait;" ::: "memory");                // nothing below may precede the kernel before this one
+  // (No griddepcontrol.launch_dependents here: letting the next solve's first-stage kernel start while this step is
+  // still running was measured - 0.19 ms per headline step - and made three units in flight on one GPU differ from
+  // the same units solved one after the other in the last bits, profiles/tuning_log_r2.md.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // nothing below may precede the kernel before this one
   const int cpg = EXACT ? CPG : (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
   const int r = tid & (PASS_T - 1), q = tid >> 6;
   if (EXACT) {   // coefficients of the padding columns stay zero for the whole step
