@@ -83,14 +83,15 @@ def test_config5_units_in_flight_are_bit_identical_to_sequential():
     seq = wl.SweepSolver(sm_limit=148 // 3)   # same share of the GPU: the reduction order of the Gram-Schmidt step depends on its grid
     ref = np.stack([seq(u) for u in units])
     seq.close()
-    solvers = [wl.SweepSolver(sm_limit=148 // 3) for _ in range(3)]
-    table, mine = sweep.run_queue(units, None, wl.SWEEP_NEV, solvers=solvers)
-    for sv in solvers:
-        sv.close()
-    assert mine == list(range(len(units)))
-    assert np.array_equal(np.isnan(ref), np.isnan(table))
-    assert np.array_equal(np.nan_to_num(ref), np.nan_to_num(table))
-    assert np.isfinite(table).sum() >= 6
+    for _ in range(4):   # which context draws which unit, and what runs beside it, differs from run to run
+        solvers = [wl.SweepSolver(sm_limit=148 // 3) for _ in range(3)]
+        table, mine = sweep.run_queue(units, None, wl.SWEEP_NEV, solvers=solvers)
+        for sv in solvers:
+            sv.close()
+        assert mine == list(range(len(units)))
+        assert np.array_equal(np.isnan(ref), np.isnan(table))
+        assert np.array_equal(np.nan_to_num(ref), np.nan_to_num(table))
+        assert np.isfinite(table).sum() >= 6
 
 
 def test_config4_scan_units_converge_as_tabulated():
