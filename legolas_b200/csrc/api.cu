@@ -490,6 +490,12 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
   return LGPU_OK;
 }
 
+// The residual vector of the Arnoldi driver is allocated with room for the padding node of an odd grid, so that the
+// solve kernels write the operator's output in place (slu_solve: x_padded).
+bool out_has_pad(lgpu_ctx* c, const cd* p) {
+  return p != nullptr && p == c->resid.p && c->resid.cap >= static_cast<size_t>(c->splan.n_pad) * BLK;
+}
+
 // x = M^-1 b on the device (b, x may alias), with optional iterative refinement
 void dev_solve(lgpu_ctx* c, const cd* b, cd* x, int refine) {
   const cd* rhs = b;
@@ -497,7 +503,7 @@ void dev_solve(lgpu_ctx* c, const cd* b, cd* x, int refine) {
     CUDA_CHECK(cudaMemcpyAsync(c->vr.p, b, sizeof(cd) * c->N, cudaMemcpyDeviceToDevice, c->stream));
     rhs = c->vr.p;
   }
-  slu_solve(c->splan, c->sdev(), rhs, x, c->stream, &c->log);
+  slu_solve(c->splan, c->sdev(), rhs, x, c->stream, &c->log, nullptr, out_has_pad(c, x));
   for (int it = 0; it < refine; ++it) {
     // e = M^-1 (b - (A - sigma B) x) ; x += e
     block_matvec(c->G, c->A.p, c->B.p, c->factor_of_B ? cd{0.0, 0.0} : cd{-1.0, 0.0},
@@ -524,7 +530,7 @@ void dev_apply_op(lgpu_ctx* c, const cd* x, cd* y, int refine) {
     RhsEll ell;
     ell.val = c->bell_rval.p; ell.col = c->bell_col.p; ell.x = x; ell.rows = c->G * BLK; ell.width = c->bell_w;
     c->log.fused_bx += 1;
-    slu_solve(c->splan, c->sdev(), nullptr, y, c->stream, &c->log, &ell);
+    slu_solve(c->splan, c->sdev(), nullptr, y, c->stream, &c->log, &ell, out_has_pad(c, y));
     return;
   }
   if (use_ell && c->bell_w >= 0 && c->bell_w <= ELL_MAX_WIDTH)
@@ -657,7 +663,7 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   // tile: entries outside the current basis must be finite (they meet zero coefficients)
   CUDA_CHECK(cudaMemsetAsync(c->V.p, 0, sizeof(cd) * c->basis.elems(), c->stream));
   c->vcur.ensure(n);
-  c->resid.ensure(n);
+  c->resid.ensure(static_cast<size_t>(n) + BLK);   // + the padding node of an odd grid (out_has_pad)
   c->Hdev.ensure(static_cast<size_t>(ncv) * ncv);
   c->Qdev.ensure(static_cast<size_t>(ncv) * ncv);
   c->Z.ensure(static_cast<size_t>(n) * nev);
@@ -1034,10 +1040,17 @@ int lgpu_apply_op_device(lgpu_ctx* ctx, const double* x_dev, double* y_dev, int3
     if (ctx->compact()) return fail(ctx, LGPU_EINVAL, "apply_op_device: mhd state vector only (device vectors are in the 16-wide layout)");
     const cd* x = reinterpret_cast<const cd*>(x_dev);
     cd* y = reinterpret_cast<cd*>(y_dev);
+    // as the Arnoldi driver issues it: from its current-vector buffer into its (padded) residual buffer
+    const size_t n = static_cast<size_t>(ctx->N);
+    ctx->vcur.ensure(n);
+    ctx->resid.ensure(n + BLK);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->vcur.p, x, n * sizeof(cd), cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int r = 0; r < repeat; ++r) dev_apply_op(ctx, x, y, refine_steps);
+    for (int r = 0; r < repeat; ++r) dev_apply_op(ctx, ctx->vcur.p, ctx->resid.p, refine_steps);
     CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(y, ctx->resid.p, n * sizeof(cd), cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    CUDA_CHECK(stream_sync(ctx));
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ms_per_application) *ms_per_application = static_cast<double>(ms) / repeat;

@@ -2014,12 +2014,12 @@ static void launch_pdl(void (*kernel)(Args...), dim3 grid, dim3 block, size_t sm
 }
 
 void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
-               LaunchLog* log, const RhsEll* ell) {
+               LaunchLog* log, const RhsEll* ell, bool x_padded) {
   configure_kernels();
   const int ns = static_cast<int>(plan.stages.size());
   const int su = first_upper_stage(plan);
   const int sf = su >= 0 ? su : first_fused_stage(plan);
-  cd* xv = plan.n_pad == plan.n ? x : d.xpad;
+  cd* xv = (plan.n_pad == plan.n || x_padded) ? x : d.xpad;
   for (int s = 0; s < sf; ++s) {
     const StageArgs a = make_stage_args(plan, d, s, b, xv, ell);
     // with the B v product fused in: plus the band of B and the vector v (12 288 + 256 bytes per grid point)

@@ -126,8 +126,10 @@ struct RhsEll {
   int rows = 0;
   int width = 0;                 // <= 8
 };
+// x_padded: x has room for n_pad * 16 entries (n odd: one padding node), the kernels write it directly and the copy
+// out of the padded scratch vector - a launch between the last solve kernel and whatever follows it - is skipped
 void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cudaStream_t stream,
-               LaunchLog* log, const RhsEll* ell = nullptr);
+               LaunchLog* log, const RhsEll* ell = nullptr, bool x_padded = false);
 // y = aa * A x + ab * B x + z : covers B*x, A*x and the refinement residual
 // r = b - (A - sigma*B) x  (aa = -1, ab = sigma, z = b)
 void block_matvec(int n, const cd* A, const cd* B, cd aa, cd ab, const cd* x, const cd* z, cd* y,
