@@ -114,6 +114,8 @@ struct lgpu_ctx {
   int bell_w = -1;              // longest row of B; -1: not built for the current B
   bool have_grid = false;       // grid_copy matches the resident matrices
   DevBuf<cd> mbox;              // mailboxes of the fused solve stages (slu.cuh)
+  DevBuf<unsigned long long> solve_flags;   // SolveSignal::flags
+  SolveSignal signal;
   unsigned long long solve_epoch = 0;
   bool factorized = false;
   bool factor_of_B = false;     // general mode: the resident factors are those of B, not of A - sigma B
@@ -142,6 +144,9 @@ struct lgpu_ctx {
     d.A = factor_of_B ? B.p : A.p; d.B = B.p; d.pairs = pairs.p; d.top = topfac.p; d.work = fwork.p; d.rhs = rhs.p;
     d.gvec = gvec.p; d.xpad = xpad.p; d.info = d_info.p;
     d.epoch = &solve_epoch; d.padmask = padmask; d.mbox = mbox.p;
+    signal.flags = solve_flags.p;
+    signal.nchunks = static_cast<int>(solve_flags.cap);
+    d.signal = &signal;
     return d;
   }
 };
@@ -455,6 +460,13 @@ int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
     c->rhs.ensure(c->splan.rhs_vecs * SB);
     c->gvec.ensure(std::max<size_t>(c->splan.pair_records, 1) * SB);
     c->xpad.ensure(static_cast<size_t>(c->splan.n_pad) * BLK);
+    {   // completion flags of the backward first stage: zero once, epochs only grow
+      const size_t need = static_cast<size_t>(std::max(1, c->splan.stages[0].nchunks));
+      if (need > c->solve_flags.cap) {
+        c->solve_flags.ensure(need);
+        CUDA_CHECK(cudaMemsetAsync(c->solve_flags.p, 0, need * sizeof(unsigned long long), c->stream));
+      }
+    }
     c->d_info.ensure(1);
     c->mbox.ensure(slu_mbox_elems(c->splan));
   }
@@ -563,11 +575,17 @@ class CudaKrylovOps final : public KrylovOps {
         krylov_scale(L, c_->resid.p, V, j, c_->vcur.p, kw, hsub, c_->stream, &c_->log);
       }
       dev_apply_op(c_, c_->vcur.p, c_->resid.p, refine_);
+      KrylovWork kws = kw;   // w = resid comes with completion flags when the solve ended with its flagged kernel
+      if (refine_ == 0 && c_->signal.last != 0 && c_->signal.last == c_->signal.epoch && c_->signal.mu >= 1 &&
+          c_->signal.x == static_cast<const void*>(c_->resid.p)) {
+        kws.wflags = c_->signal.flags; kws.wepoch = c_->signal.last;
+        kws.wtile_shift = c_->signal.mu - 1; kws.wnchunks = c_->splan.stages[0].nchunks;
+      }
       cd* hcol = H + static_cast<size_t>(j) * ncv_;
       // the fused step also produces v_{j+1} when there is a next step in this batch
       const int newcol = j + 1 < m ? j + 1 : -1;
       cd* hnext = H + static_cast<size_t>(j) * ncv_ + j + 1;
-      have_vj = krylov_cgs2_step(L, V, j + 1, c_->resid.p, kw, hcol, newcol, c_->vcur.p, hnext, c_->stream,
+      have_vj = krylov_cgs2_step(L, V, j + 1, c_->resid.p, kws, hcol, newcol, c_->vcur.p, hnext, c_->stream,
                                  &c_->log);
       if (have_vj) {
         have_vj = newcol >= 0;

@@ -245,6 +245,10 @@ struct CgsArgs {
   int newcol;                    // >= 0: V(:, newcol) = vplain = w / ||w|| and *hsub = ||w||
   cd* vplain;
   cd* hsub;
+  // per-chunk completion flags of the kernel that produces w (KrylovWork::wflags), or null
+  const unsigned long long* wflags;
+  unsigned long long wepoch;
+  int wtile_shift, wnchunks;
 };
 
 // Device-wide barrier of the consumer threads (pattern of cooperative groups' grid sync): the CTA
@@ -365,11 +369,28 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
         if (wbytes) bulk_g2s(sb + ncopy * PASS_T, a.w + static_cast<size_t>(t) * PASS_T, wbytes, &full[sg]);
       };
       // Programmatic dependent launch (krylov_cgs2_step): this CTA may be running while the kernel that produces w
-      // is still at work; nothing is read before that kernel has completed.  (The basis tiles could be requested
-      // earlier only with a completion protocol of their own: the newest column is written by the previous step's
-      // launch, and an early start is ordered after the START of the kernels in between, not after their end.)
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      for (int i = 0; i < nt; ++i) fill(i, cgs_fill_number(1, i, nt, sd), true);
+      // is still at work.  Without completion flags nothing is read before that kernel has completed.  With them
+      // (the solve's last kernel publishes, chunk by chunk, that its part of w is final) a tile is requested as soon
+      // as its chunk is done - the first pass starts while that kernel's last CTAs are still running, and there is
+      // no grid-completion latency between the two.  The first flag this lane sees also orders everything it reads
+      // after the completion of the whole chain before that chunk (solve kernels, the previous step's launch that
+      // wrote the newest basis column): each of them waited for its predecessor's end.
+      if (a.wflags == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
+      int have_chunk = -1;
+      for (int i = 0; i < nt; ++i) {
+        if (a.wflags != nullptr) {
+          const int c = min((t0 + i) >> a.wtile_shift, a.wnchunks - 1);
+          if (c != have_chunk) {
+            unsigned long long v;
+            do {
+              asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wflags + c) : "memory");
+            } while (v < a.wepoch);
+            asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below read what generic stores wrote
+            have_chunk = c;
+          }
+        }
+        fill(i, cgs_fill_number(1, i, nt, sd), true);
+      }
       for (int i = nt - S - 1; i >= 0; --i) fill(i, cgs_fill_number(2, i, nt, sd), false);
       for (int i = S; i < nt; ++i) fill(i, cgs_fill_number(3, i, nt, sd), false);
     }
@@ -379,7 +400,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   // (No griddepcontrol.launch_dependents here: letting the next solve's first-stage kernel start while this step is
   // still running was measured - 0.19 ms per headline step - and made three units in flight on one GPU differ from
   // the same units solved one after the other in the last bits, profiles/tuning_log_r2.md.)
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // nothing below may precede the kernel before this one
+  // nothing below may precede the kernel before this one - unless w comes with completion flags: then the consumers
+  // touch global memory only after the first device-wide barrier, i.e. after every tile of w has been loaded
+  if (a.wflags == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int cpg = EXACT ? CPG : (ncols + PASS_GROUPS - 1) / PASS_GROUPS;
   const int r = tid & (PASS_T - 1), q = tid >> 6;
   if (EXACT) {   // coefficients of the padding columns stay zero for the whole step
@@ -973,6 +996,25 @@ static void launch_cgs2(const CgsArgs& a, int grid, size_t smem, cudaStream_t st
   // GPU (SM cap set) keeps the plain launch: its admission ticket counts the solve kernels OR this grid, not both.
   static const bool pdl_env = [] { const char* e = std::getenv("LGPU_PDL"); return !(e && e[0] == '0'); }();
   static bool pdl_ok = true;   // cleared if the driver rejects the attribute pair
+  if (a.wflags != nullptr) {
+    // With completion flags the CTAs must be able to start while the solve's last kernel is still running: a
+    // cooperative grid is started only once ALL its CTAs fit, i.e. after that kernel has drained (timeline: all 148
+    // CTAs start 4 us after its last CTA ends).  A plain programmatic launch instead: the CTAs take the SMs one by
+    // one as they become free.  They are all resident in the end - this context is alone on the GPU (its admission
+    // ticket covers every SM), there is one CTA per SM, and the kernel they wait for never waits for them.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(PASS_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, krylov_cgs2_kernel<CPG>, a));
+    return;
+  }
   if (pdl && pdl_env && pdl_ok) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1022,6 +1064,14 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   a.bar_base = *work.gbar_count;
   *work.gbar_count += 2ull * grid;
   a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
+  // completion flags only for a context alone on the GPU, with programmatic launches on, one CTA per SM
+  static const bool flags_env = [] {
+    const char* e = std::getenv("LGPU_CGS2_FLAGS"); const char* p = std::getenv("LGPU_PDL");
+    return !(e && e[0] == '0') && !(p && p[0] == '0');
+  }();
+  if (flags_env && work.wflags != nullptr && work.grid_cap <= 0 && grid <= sm_count()) {
+    a.wflags = work.wflags; a.wepoch = work.wepoch; a.wtile_shift = work.wtile_shift; a.wnchunks = work.wnchunks;
+  }
   const size_t smem = cgs2_smem(ncopy, nstages, tiles_max);
   // one orthogonalisation at basis size j = two passes, 2 (j + 2) 256 G bytes
   log->begin(LK_CGS2, 16.0 * L.n * (2.0 * ncols + 4.0));

@@ -45,6 +45,12 @@ struct KrylovWork {
   unsigned long long* gbar;         // device-wide barrier counter of the fused step kernel (or null)
   unsigned long long* gbar_count;   // host: value the counter will have when the next launch starts
   int grid_cap = 0;                 // > 0: the fused step kernel uses at most this many CTAs (lgpu_set_sm_limit)
+  // w was produced in place by a solve whose last kernel publishes per-chunk completion flags (slu.cuh: SolveSignal):
+  // rows [512 c .. ) << ... of w are final once wflags[c] >= wepoch.  Null: wait for the kernel before the step.
+  const unsigned long long* wflags = nullptr;
+  unsigned long long wepoch = 0;
+  int wtile_shift = 0;              // chunk of tile t = min(t >> wtile_shift, wnchunks - 1)
+  int wnchunks = 0;
 };
 // CTAs of the fused step kernel (one per SM, all of them must be resident: it has a device-wide barrier)
 int krylov_cgs2_grid(int ntiles, int grid_cap);

@@ -138,6 +138,8 @@ struct StageArgs {
   int poll_z;        // boundary unknowns of a chunk come from zbox (polled) instead of xv
   RhsEll ell;        // ell.x != nullptr: the right-hand side is B v, formed on the fly (b is not read)
   int fin_is_rhs;    // first stage: fin points into the right-hand side itself
+  unsigned long long* done_flags;   // backward first stage: SolveSignal::flags (or null)
+  unsigned long long done_epoch;
 };
 
 // entry idx of the right-hand side
@@ -734,6 +736,13 @@ __global__ void __launch_bounds__(RING_THREADS, 3) slu_bwd_stage_kernel(StageArg
   RingPos pos{0, 0u}, upos{0, 0u};
   bwd_stage_body(a, blockIdx.x, rg, pos, ur, upos, z, part);
   TRACE_MARK(2, 2);
+  if (a.done_flags != nullptr) {   // this chunk's part of the solution is final (SolveSignal)
+    consumer_sync();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(a.done_flags + blockIdx.x), "l"(a.done_epoch) : "memory");
+    }
+  }
 }
 
 // The narrow upper stages and the top system in ONE cooperative launch (grid = chunks of the first
@@ -2108,8 +2117,19 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     }
     log->end();
   }
+  if (d.signal != nullptr) {
+    ++d.signal->epoch;
+    d.signal->last = 0;
+  }
   for (int s = sf - 1; s >= 0; --s) {
-    const StageArgs a = make_stage_args(plan, d, s, b, xv, ell);
+    StageArgs a = make_stage_args(plan, d, s, b, xv, ell);
+    if (s == 0 && d.signal != nullptr && d.signal->flags != nullptr && xv == x && a.nchunks <= d.signal->nchunks) {
+      a.done_flags = d.signal->flags;
+      a.done_epoch = d.signal->epoch;
+      d.signal->last = d.signal->epoch;
+      d.signal->mu = a.mu;
+      d.signal->x = x;
+    }
     log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
     const RingShape sh = bwd_shape(a, false);
     launch_pdl(slu_bwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns, sh.nu);

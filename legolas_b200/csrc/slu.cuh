@@ -90,6 +90,20 @@ struct SluPlan {
 SluPlan make_slu_plan(int n, int first_stage_mu, int next_stage_mu, int top_max_rows);
 int slu_coresident_demand(const SluPlan& plan);   // SMs a running solve may hold while waiting (see slu.cu)
 
+// Completion flags of the last kernel of a solve (backward first stage), for a consumer that does not want to wait
+// for the whole grid: chunk c of that kernel stores `epoch` into flags[c] (release) once every entry of the solution
+// it owns - rows 32 * (c << mu) ... of x, boundary nodes included - is final.  `epoch` counts the solves of the
+// context and never goes back; `last` is the epoch of the most recent solve IF that solve ended with such a kernel
+// writing x in place (0 otherwise: the consumer must then wait for the grid).
+struct SolveSignal {
+  unsigned long long* flags = nullptr;   // device, >= chunks of the first stage, zero at allocation
+  unsigned long long epoch = 0;          // host
+  unsigned long long last = 0;           // host
+  const void* x = nullptr;               // host: the vector that solve wrote
+  int mu = 0;                            // rows of the first stage's chunks = 1 << mu (32 entries of x each)
+  int nchunks = 0;
+};
+
 struct SluDevice {
   const cd* A;          // (n, 3, 256) blocks
   const cd* B;
@@ -109,6 +123,7 @@ struct SluDevice {
   cd* mbox;
   uint32_t padmask;     // bit i: row/column i of every 16-wide block belongs to a variable that is not
                         // in the state vector (hd / hd-1d): treated as a decoupled identity row
+  SolveSignal* signal = nullptr;   // host; may be null
 };
 inline size_t slu_mbox_half(const SluPlan& p) { return (p.rhs_vecs + static_cast<size_t>(p.K)) * SB; }
 inline size_t slu_mbox_elems(const SluPlan& p) { return 2 * slu_mbox_half(p); }

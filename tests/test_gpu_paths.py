@@ -67,6 +67,8 @@ def default_result():
     {"LGPU_GEMM_MMA": "0", "LGPU_GEMM_ROWS": "0"},   # shared-memory tiled restart GEMM
     {"LGPU_SLU_UPPER": "0"},                     # upper solve stages streamed through rings (cooperative launch)
     {"LGPU_BX_FUSE": "0"},                       # separate launch for the B x product
+    {"LGPU_CGS2_FLAGS": "0"},                    # Gram-Schmidt step waits for the whole solve kernel, not for per-chunk flags
+    {"LGPU_PDL": "0"},                           # no programmatic dependent launches at all
     {"LGPU_MERGE_LOOKAHEAD": "0"},               # factorisation without look-ahead (panel, then update)
     {"LGPU_SLU_MU0": "3", "LGPU_SLU_MU1": "3", "LGPU_SLU_TOP": "32"},  # another stage tree
 ], ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
@@ -85,5 +87,8 @@ def test_variant_matches_default(default_result, env_extra):
         # variants that leave the factorisation / solve kernels alone, or claim the same operations per entry in the same
         # order (look-ahead), must reproduce the solve bit for bit
         if set(env_extra) <= {"LGPU_MERGE_LOOKAHEAD", "LGPU_GEMM_MMA", "LGPU_GEMM_ROWS", "LGPU_CGS2_FUSED", "LGPU_CGS2_EXACT",
-                              "LGPU_B_ELL", "LGPU_BX_FUSE"}:
+                              "LGPU_B_ELL", "LGPU_BX_FUSE", "LGPU_CGS2_FLAGS", "LGPU_PDL"}:
             assert got[name]["solve_sha"] == ref["solve_sha"], name
+        # variants that only change how launches are ordered and overlapped must not change a single bit of the run
+        if set(env_extra) <= {"LGPU_CGS2_FLAGS", "LGPU_PDL"}:
+            assert np.array_equal(a, b), (name, np.abs(a - b).max())
