@@ -345,6 +345,15 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
   }
+  // completion flag of the first tile's chunk: polled by the producer lane while thread 0 sets up the barriers
+  int have_chunk = -1;
+  if (a.wflags != nullptr && tid == 8 * 32 && nt > 0) {
+    have_chunk = min(t0 >> a.wtile_shift, a.wnchunks - 1);
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wflags + have_chunk) : "memory");
+    } while (v < a.wepoch);
+  }
   __syncthreads();
   if (warp == 8) {
     // ---- producer (one lane).  Local tile i always lives in ring slot i % S, and the passes run
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
       // after the completion of the whole chain before that chunk (solve kernels, the previous step's launch that
       // wrote the newest basis column): each of them waited for its predecessor's end.
       if (a.wflags == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
-      int have_chunk = -1;
+      else asm volatile("fence.proxy.async;" ::: "memory");
       for (int i = 0; i < nt; ++i) {
         if (a.wflags != nullptr) {
           const int c = min((t0 + i) >> a.wtile_shift, a.wnchunks - 1);
