@@ -587,6 +587,7 @@ class CudaKrylovOps final : public KrylovOps {
       cd* hnext = H + static_cast<size_t>(j) * ncv_ + j + 1;
       have_vj = krylov_cgs2_step(L, V, j + 1, c_->resid.p, kws, hcol, newcol, c_->vcur.p, hnext, c_->stream,
                                  &c_->log);
+      rnorm_in_h_ = have_vj && j + 1 == ncv_;   // the fused step left ||resid|| in the slot behind H (hnext of the last column)
       if (have_vj) {
         have_vj = newcol >= 0;
       } else {
@@ -599,12 +600,15 @@ class CudaKrylovOps final : public KrylovOps {
 
   void fetch(int k, int m, cplx* H, int ldh, double* rnorm) override {
     const size_t cnt = static_cast<size_t>(ncv_) * ncv_;
-    c_->h_stage.ensure(cnt);
-    CUDA_CHECK(cudaMemcpyAsync(c_->h_stage.p, c_->Hdev.p, cnt * sizeof(cd), cudaMemcpyDeviceToHost,
+    c_->h_stage.ensure(cnt + 1);
+    // one copy when the residual norm travels with H (the usual case), a second one for it otherwise
+    const bool one = rnorm_in_h_ && m == ncv_;
+    CUDA_CHECK(cudaMemcpyAsync(c_->h_stage.p, c_->Hdev.p, (cnt + (one ? 1 : 0)) * sizeof(cd), cudaMemcpyDeviceToHost,
                                c_->stream));
-    CUDA_CHECK(cudaMemcpyAsync(c_->h_scal.p, c_->kscal.p, sizeof(double), cudaMemcpyDeviceToHost,
-                               c_->stream));
+    if (!one)
+      CUDA_CHECK(cudaMemcpyAsync(c_->h_scal.p, c_->kscal.p, sizeof(double), cudaMemcpyDeviceToHost, c_->stream));
     CUDA_CHECK(stream_sync(c_));
+    if (one) c_->h_scal.p[0] = c_->h_stage.p[cnt].x;
     for (int j = k; j < m; ++j) {
       for (int i = 0; i <= j; ++i) {
         const cd v = c_->h_stage.p[static_cast<size_t>(j) * ncv_ + i];
@@ -654,6 +658,7 @@ class CudaKrylovOps final : public KrylovOps {
   lgpu_ctx* c_;
   int ncv_;
   int refine_;
+  bool rnorm_in_h_ = false;
 };
 
 // general = false: OP = (A - sigma B)^-1 B, omega = sigma + 1/nu  (smod_arpack_shift_invert.f08)
@@ -682,7 +687,7 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   CUDA_CHECK(cudaMemsetAsync(c->V.p, 0, sizeof(cd) * c->basis.elems(), c->stream));
   c->vcur.ensure(n);
   c->resid.ensure(static_cast<size_t>(n) + BLK);   // + the padding node of an odd grid (out_has_pad)
-  c->Hdev.ensure(static_cast<size_t>(ncv) * ncv);
+  c->Hdev.ensure(static_cast<size_t>(ncv) * ncv + 1);   // + ||resid|| behind the last column (CudaKrylovOps::fetch)
   c->Qdev.ensure(static_cast<size_t>(ncv) * ncv);
   c->Z.ensure(static_cast<size_t>(n) * nev);
   ensure_krylov_work(c);

@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
   const double rnorm = s_norm;
   if (blockIdx.x == 0 && tid == 0) {
     a.scal[0] = rnorm;
-    if (a.newcol >= 0 && a.hsub) *a.hsub = cd{rnorm, 0.0};
+    if (a.hsub) *a.hsub = cd{rnorm, 0.0};   // H(j + 1, j); for the last column of a full basis: the slot behind the matrix
   }
 
   CGS_MARK(9);
