@@ -570,10 +570,16 @@ def run_sharded_sections(args, rank, world, local_rank, device):
     n_op, conv = total([sum(sv.n_op for sv in solvers), sum(sv.converged for sv in solvers)])
     for sv in solvers:
         sv.close()
+    # the two passes (different queue order, different neighbours on the GPU) against each other: units in flight must
+    # not see each other (profiles/tuning_log_r2.md, "several contexts in flight")
+    a, b = np.nan_to_num(cost_table[:, 0]), np.nan_to_num(table[:, 0])
+    same_nan = np.isnan(cost_table[:, 0].real) == np.isnan(table[:, 0].real)
+    repeat = {"passes_compared": 2, "units_bit_identical": int(np.sum(same_nan & (a == b))),
+              "units_within_1e-8": int(np.sum(same_nan & (np.abs(a - b) <= 1e-8 * np.maximum(np.abs(a), 1e-300))))}
     out["sweep"] = {"workload": f"config 5: kelvin_helmholtz_cd G={wl.SWEEP_GRIDPTS}, {len(units)}-point (k2,k3) sweep, per-unit shift from "
                                 f"a coarse QR-invert pre-scan, nev={wl.SWEEP_NEV} ncv={wl.SWEEP_NCV} maxiter={wl.SWEEP_MAXITER}",
                     "units": len(units), "seconds": sec, "units_per_s": len(units) / sec, "n_op_total": int(n_op),
-                    "units_converged": int(conv), "units_in_flight_per_gpu": workers,
+                    "units_converged": int(conv), "units_in_flight_per_gpu": workers, "repeatability": repeat,
                     "seconds_per_rank": last_pass["seconds_per_rank"],
                     "scheduling": "shared queue, longest first by the operator applications of the untimed pass",
                     "max_growth_rate": float(np.nanmax(table.imag))}

@@ -42,6 +42,10 @@ struct DevBuf {
     release();
     CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
     cap = count;
+    // debugging aid: LGPU_DBG_POISON=<byte> fills every fresh device allocation with that byte (255: NaNs), so that
+    // a read of memory nothing has written yet shows up in the results instead of depending on what the allocator returns
+    static const int poison = [] { const char* e = std::getenv("LGPU_DBG_POISON"); return e ? std::atoi(e) : -1; }();
+    if (poison >= 0) CUDA_CHECK(cudaMemset(p, poison & 0xff, std::max<size_t>(count, 1) * sizeof(T)));
   }
 };
 
@@ -62,6 +66,42 @@ struct PinnedBuf {
 int env_int(const char* name, int fallback) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : fallback;
+}
+
+// debugging aid: LGPU_DBG_SERIAL=<mask> lets only one context of the process at a time be in a phase
+// (bit 0 assembly, bit 1 factorisation, bit 2 Arnoldi iteration) - which phase is sensitive to neighbours on the GPU?
+struct DbgSerial {
+  std::mutex* m = nullptr;
+  explicit DbgSerial(int phase) {
+    static const int mask = [] { const char* e = std::getenv("LGPU_DBG_SERIAL"); return e ? std::atoi(e) : 0; }();
+    static std::mutex mu[3];
+    if ((mask >> phase) & 1) { m = &mu[phase]; m->lock(); }
+  }
+  ~DbgSerial() { if (m) m->unlock(); }
+};
+
+inline bool dbg_serial_steps() {
+  static const bool on = [] { const char* e = std::getenv("LGPU_DBG_SERIAL"); return e && (std::atoi(e) & 8); }();
+  return on;
+}
+inline std::mutex& dbg_step_mutex() { static std::mutex m; return m; }
+// debugging aid: LGPU_DBG_DUAL=1 runs every operator application and every fused Gram-Schmidt step of the Arnoldi
+// driver twice on the same inputs and counts the 8-byte words in which the two outputs differ
+__global__ void dbg_compare_kernel(const unsigned long long* a, const unsigned long long* b, size_t n64,
+                                   unsigned long long* counter) {
+  unsigned long long bad = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n64;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    bad += a[i] != b[i];
+  if (bad) atomicAdd(counter, bad);
+}
+inline bool dbg_dual() {
+  static const bool on = std::getenv("LGPU_DBG_DUAL") != nullptr;
+  return on;
+}
+inline void dbg_compare(const cd* a, const cd* b, size_t n, unsigned long long* counter, cudaStream_t stream) {
+  dbg_compare_kernel<<<64, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(a),
+                                             reinterpret_cast<const unsigned long long*>(b), 2 * n, counter);
 }
 
 double now_ms() {
@@ -131,6 +171,8 @@ struct lgpu_ctx {
   DevBuf<unsigned long long> kgbar;
   unsigned long long kgbar_count = 0;
   PinnedBuf<cd> h_stage, h_upload;
+  DevBuf<cd> dbg_buf;                       // LGPU_DBG_DUAL scratch
+  DevBuf<unsigned long long> dbg_cnt;       // LGPU_DBG_DUAL mismatch counters
   PinnedBuf<double> h_scal;
 
   LaunchLog log;
@@ -353,6 +395,7 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
                 const FieldPtrs& fields) {
   if (s->physics_type < 0 || s->physics_type > 2)
     return fail(c, LGPU_EINVAL, "physics_type must be 0 (mhd), 1 (hd) or 2 (hd-1d)");
+  DbgSerial dbg_serial(0);
   const int G = s->gridpts;
   c->settings = *s;
   c->G = G;
@@ -449,6 +492,7 @@ int do_assemble(lgpu_ctx* c, const lgpu_settings* s, const double* d_grid, const
 // factors of A - sigma B, or (of_B, general mode: sigma ignored) of B itself
 int do_factorize(lgpu_ctx* c, cd sigma, bool of_B = false) {
   if (!c->assembled()) return fail(c, LGPU_ESTATE, "factorize: matrices not assembled");
+  DbgSerial dbg_serial(1);
   c->factor_of_B = of_B;
   if (of_B) sigma = cd{0.0, 0.0};
   if (c->splan.n != c->G) {
@@ -574,9 +618,18 @@ class CudaKrylovOps final : public KrylovOps {
         cd* hsub = j > 0 ? H + static_cast<size_t>(j - 1) * ncv_ + j : nullptr;
         krylov_scale(L, c_->resid.p, V, j, c_->vcur.p, kw, hsub, c_->stream, &c_->log);
       }
+      std::unique_lock<std::mutex> dbg_step_lock;   // LGPU_DBG_SERIAL bit 3: one Arnoldi step of the process at a time
+      if (dbg_serial_steps()) dbg_step_lock = std::unique_lock<std::mutex>(dbg_step_mutex());
       dev_apply_op(c_, c_->vcur.p, c_->resid.p, refine_);
+      const bool dual = dbg_dual() && c_->dbg_cnt.p != nullptr;
+      cd* dbg_win = nullptr; cd* dbg_wout = nullptr; cd* dbg_h = nullptr;
+      if (dual) {
+        dbg_win = c_->dbg_buf.p; dbg_wout = dbg_win + n; dbg_h = dbg_wout + n;
+        dev_apply_op(c_, c_->vcur.p, dbg_win, refine_);                       // second evaluation of w = OP v
+        dbg_compare(c_->resid.p, dbg_win, n, c_->dbg_cnt.p + 0, c_->stream);
+      }
       KrylovWork kws = kw;   // w = resid comes with completion flags when the solve ended with its flagged kernel
-      if (refine_ == 0 && c_->signal.last != 0 && c_->signal.last == c_->signal.epoch && c_->signal.mu >= 1 &&
+      if (!dual && refine_ == 0 && c_->signal.last != 0 && c_->signal.last == c_->signal.epoch && c_->signal.mu >= 1 &&
           c_->signal.x == static_cast<const void*>(c_->resid.p)) {
         kws.wflags = c_->signal.flags; kws.wepoch = c_->signal.last;
         kws.wtile_shift = c_->signal.mu - 1; kws.wnchunks = c_->splan.stages[0].nchunks;
@@ -587,7 +640,16 @@ class CudaKrylovOps final : public KrylovOps {
       cd* hnext = H + static_cast<size_t>(j) * ncv_ + j + 1;
       have_vj = krylov_cgs2_step(L, V, j + 1, c_->resid.p, kws, hcol, newcol, c_->vcur.p, hnext, c_->stream,
                                  &c_->log);
+      if (dual && have_vj) {   // the same step once more on the same w: outputs must agree bit for bit
+        CUDA_CHECK(cudaMemcpyAsync(dbg_wout, c_->resid.p, sizeof(cd) * n, cudaMemcpyDeviceToDevice, c_->stream));
+        CUDA_CHECK(cudaMemcpyAsync(dbg_h, hcol, sizeof(cd) * (j + 2), cudaMemcpyDeviceToDevice, c_->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c_->resid.p, dbg_win, sizeof(cd) * n, cudaMemcpyDeviceToDevice, c_->stream));
+        krylov_cgs2_step(L, V, j + 1, c_->resid.p, kws, hcol, newcol, c_->vcur.p, hnext, c_->stream, &c_->log);
+        dbg_compare(c_->resid.p, dbg_wout, n, c_->dbg_cnt.p + 1, c_->stream);
+        dbg_compare(hcol, dbg_h, j + 2, c_->dbg_cnt.p + 2, c_->stream);
+      }
       rnorm_in_h_ = have_vj && j + 1 == ncv_;   // the fused step left ||resid|| in the slot behind H (hnext of the last column)
+      if (dbg_step_lock.owns_lock()) CUDA_CHECK(cudaStreamSynchronize(c_->stream));
       if (have_vj) {
         have_vj = newcol >= 0;
       } else {
@@ -679,6 +741,7 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
 
   int rc = do_factorize(c, cd{cfg->sigma_re, cfg->sigma_im}, general);
   if (rc != LGPU_OK) return rc;
+  DbgSerial dbg_serial(2);
   const int ncv = cfg->ncv, nev = cfg->nev;
   c->basis = make_basis_layout(n, ncv);
   c->V.ensure(c->basis.elems());
@@ -693,6 +756,11 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   ensure_krylov_work(c);
   CUDA_CHECK(cudaMemsetAsync(c->Hdev.p, 0, sizeof(cd) * ncv * ncv, c->stream));
   vec_in(c, resid0, resid_on_device, c->resid.p);
+  if (dbg_dual()) {
+    c->dbg_buf.ensure(2 * static_cast<size_t>(n) + BLK + ncv + 2);
+    c->dbg_cnt.ensure(4);
+    CUDA_CHECK(cudaMemsetAsync(c->dbg_cnt.p, 0, 4 * sizeof(unsigned long long), c->stream));
+  }
 
   IramConfig ic;
   ic.nev = nev; ic.ncv = ncv; ic.maxiter = cfg->maxiter; ic.tol = cfg->tol;
@@ -702,6 +770,14 @@ int do_shift_invert(lgpu_ctx* c, const lgpu_arnoldi* cfg, const double* resid0, 
   const double t0 = now_ms();
   IramResult res = iram.run(ops, ic);
   CUDA_CHECK(stream_sync(c));
+  if (dbg_dual()) {
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpy(cnt, c->dbg_cnt.p, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (cnt[0] | cnt[1] | cnt[2])
+      std::fprintf(stderr, "[lgpu dual] ctx %p sigma (%g, %g): words differing between two evaluations: operator %llu, "
+                   "step w %llu, step h %llu (n_op %d)\n", static_cast<void*>(c), cfg->sigma_re, cfg->sigma_im, cnt[0], cnt[1],
+                   cnt[2], res.n_op);
+  }
   const double t1 = now_ms();
   const double nan = std::numeric_limits<double>::quiet_NaN();
   for (int k = 0; k < nev; ++k) {

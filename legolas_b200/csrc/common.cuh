@@ -140,7 +140,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   } while (!ok);
 }
+// The destination is a ring slot that consumer warps have just read with ordinary (generic-proxy) loads and released
+// through an mbarrier; the copy writes it through the async proxy.  The mbarrier orders the release against the
+// producer lane's wait, not the two proxies against each other: without the cross-proxy fence a copy could land while
+// a consumer's loads of the previous contents were still outstanding, and that consumer then worked on the NEXT record.
+// Never seen with one context on the GPU, but with CTAs of other contexts on the same SMs it made one operator
+// application in ~10^3 wrong (profiles/tuning_log_r2.md, "several contexts in flight").  One fence per copy, issued by
+// the producer lane after it has acquired the slot.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("fence.proxy.async;" ::: "memory");
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
@@ -159,6 +167,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
 }
 __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
                                               uint64_t policy) {
+#ifdef LGPU_DBG_SAFE_TMA   // debugging variant: no L2 hint
+  bulk_g2s(dst, src, bytes, bar);
+  return;
+#endif
+  asm volatile("fence.proxy.async;" ::: "memory");   // see bulk_g2s
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");

@@ -2003,12 +2003,14 @@ int slu_coresident_demand(const SluPlan& plan) {
 // Programmatic dependent launch of the solve's kernels: a kernel may start while its predecessor on
 // the stream is still running; it copies its first factor records (static data) and then blocks in
 // griddepcontrol.wait until the predecessor has completed.
-static bool pdl_enabled() {
+// edge: 0 forward stage kernels, 1 upper-stage kernel, 2 backward stage kernels (LGPU_PDL_MASK: debugging, default all)
+static bool pdl_enabled(int edge) {
   static const bool on = [] { const char* e = std::getenv("LGPU_PDL"); return !(e && e[0] == '0'); }();
-  return on;
+  static const int mask = [] { const char* e = std::getenv("LGPU_PDL_MASK"); return e ? std::atoi(e) : 7; }();
+  return on && ((mask >> edge) & 1);
 }
 template <typename... Args>
-static void launch_pdl(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+static void launch_pdl(int edge, void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -2018,7 +2020,7 @@ static void launch_pdl(void (*kernel)(Args...), dim3 grid, dim3 block, size_t sm
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(edge) ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, args...));
 }
 
@@ -2035,7 +2037,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     log->begin(s == 0 ? LK_FWD0 : LK_FWD,
                stage_algo_bytes(plan, s, 7936.0) + (s == 0 && ell != nullptr ? 12544.0 * plan.n : 0.0));
     const RingShape sh = fwd_shape(a);
-    launch_pdl(slu_fwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns);
+    launch_pdl(0, slu_fwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns);
     log->end();
   }
   double top_bytes = stage_algo_bytes(plan, ns - 1, 24064.0) + 2.0 * 24064.0 * 2;
@@ -2101,7 +2103,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
           u.pf_count = static_cast<int>(recs);
         }
       }
-      launch_pdl(slu_upper_kernel, dim3(ctas), dim3(UP_THREADS), UP_SMEM, stream, u);
+      launch_pdl(1, slu_upper_kernel, dim3(ctas), dim3(UP_THREADS), UP_SMEM, stream, u);
     } else {
       FusedArgs f{};
       f.nst = ns - sf;
@@ -2132,7 +2134,7 @@ void slu_solve(const SluPlan& plan, const SluDevice& d, const cd* b, cd* x, cuda
     }
     log->begin(s == 0 ? LK_BWD0 : LK_BWD, stage_algo_bytes(plan, s, 16128.0));
     const RingShape sh = bwd_shape(a, false);
-    launch_pdl(slu_bwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns, sh.nu);
+    launch_pdl(2, slu_bwd_stage_kernel, dim3(a.nchunks), dim3(RING_THREADS), sh.bytes, stream, a, sh.ns, sh.nu);
     log->end();
   }
   log->launches += 2 * sf + 1;

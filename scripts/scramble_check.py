@@ -1,0 +1,19 @@
+"""Scratch: ONE context, the 12 units solved repeatedly; with LGPU_DBG_SCRAMBLE=1 the shared memory of every SM holds a
+different NaN pattern before every operator application and Gram-Schmidt step - identical passes = no kernel reads
+shared memory it has not written."""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+from legolas_b200 import workloads as wl
+passes = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+units = wl.sweep_units(12)
+s = wl.SweepSolver(sm_limit=148 // 3)
+ref = np.stack([s(u) for u in units])
+bad = 0
+for p in range(passes):
+    t = np.stack([s(u) for u in units])
+    same = np.array_equal(np.nan_to_num(ref), np.nan_to_num(t)) and np.array_equal(np.isnan(ref), np.isnan(t))
+    bad += not same
+    if not same:
+        print("pass", p, "differs: max", np.abs(np.nan_to_num(ref) - np.nan_to_num(t)).max(), "nan rows", int(np.isnan(t.real).sum()))
+print("reference nan rows", int(np.isnan(ref.real).sum()), "passes that differ:", bad, "of", passes)
