@@ -120,8 +120,7 @@ krylov_pass_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, int nstag
           const int c = q * cpg + j;
           v[j] = (j < cpg && c < ncols && valid) ? sb[c * PASS_T + r] : cd{0.0, 0.0};
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);   // the tile now lives in registers
+        mbar_release_slot(&empty[stage], lane);   // the tile now lives in registers
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       if (UPDATE && ncols > 0) {
@@ -445,8 +444,8 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     }
     // the tile now lives in registers: release the slot unless the next pass starts with it
     const bool keep = (pass == 1 && i >= nt - S) || (pass == 2 && i < S);
-    __syncwarp();
-    if (!keep && lane == 0) mbar_arrive(&empty[sg]);
+    if (!keep) mbar_release_slot(&empty[sg], lane);
+    else __syncwarp();
   };
   auto load_tile = [&](int pass, int i, bool want_w, cd& wi) { load_tile_into(v, pass, i, want_w, wi); };
   // Two tiles per CTA barrier (passes 2 and 3 of the predicate-free variants): the chain of a tile - registers,

@@ -127,6 +127,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// Release of a ring slot that a bulk copy (async proxy) will refill, by a warp that has read it with ordinary
+// (generic-proxy) loads.  The mbarrier orders the arrival against the producer lane's wait, not the two proxies against
+// each other: a warp can arrive while its loads of the slot are still outstanding, and without the cross-proxy fence
+// the refill could land first - the warp then worked on the NEXT record.  Never seen with one context on the GPU, but
+// with CTAs of other contexts on the same SMs one operator application in ~10^3 came out wrong
+// (profiles/tuning_log_r2.md, "several contexts in flight").  Every lane fences its own loads, one lane arrives.
+// (-DLGPU_FENCE_AT_PRODUCER: the fence in front of every copy instead, issued by the producer lane after it has
+// acquired the slot - equally effective, but it keeps the copies of a ring from overlapping: 45 -> 58 us per
+// Gram-Schmidt step.)
+__device__ __forceinline__ void mbar_release_slot(uint64_t* empty, int lane) {
+#ifndef LGPU_FENCE_AT_PRODUCER
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty);
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes)
                : "memory");
@@ -140,15 +156,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                  : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   } while (!ok);
 }
-// The destination is a ring slot that consumer warps have just read with ordinary (generic-proxy) loads and released
-// through an mbarrier; the copy writes it through the async proxy.  The mbarrier orders the release against the
-// producer lane's wait, not the two proxies against each other: without the cross-proxy fence a copy could land while
-// a consumer's loads of the previous contents were still outstanding, and that consumer then worked on the NEXT record.
-// Never seen with one context on the GPU, but with CTAs of other contexts on the same SMs it made one operator
-// application in ~10^3 wrong (profiles/tuning_log_r2.md, "several contexts in flight").  One fence per copy, issued by
-// the producer lane after it has acquired the slot.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+#ifdef LGPU_FENCE_AT_PRODUCER
   asm volatile("fence.proxy.async;" ::: "memory");
+#endif
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
@@ -171,7 +182,9 @@ __device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32
   bulk_g2s(dst, src, bytes, bar);
   return;
 #endif
-  asm volatile("fence.proxy.async;" ::: "memory");   // see bulk_g2s
+#ifdef LGPU_FENCE_AT_PRODUCER
+  asm volatile("fence.proxy.async;" ::: "memory");
+#endif
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
       ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");

@@ -257,8 +257,7 @@ __device__ __forceinline__ const cd* ring_acquire(const Ring& rg, const RingPos&
   return rg.slots + p.slot * rg.stride;
 }
 __device__ __forceinline__ void ring_release(const Ring& rg, RingPos& p, int lane) {
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&rg.empty[p.slot]);
+  mbar_release_slot(&rg.empty[p.slot], lane);
   advance(rg, p);
 }
 // producer lane: next slot of the ring <- `count` complex entries at src.  `p.phase` is the
@@ -518,8 +517,7 @@ __device__ __forceinline__ void chunk_backward(const StageArgs& a, const Ring& r
         const int qm = 2 * (i0 + warp) * s + s;
         z[qm * SB + lane] = r;
         publish_node(a, unknown_index(a, r0 + qm), lane, r);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ur.empty[mine.slot]);
+        mbar_release_slot(&ur.empty[mine.slot], lane);
       }
       consumer_sync();
     }
