@@ -248,6 +248,7 @@ struct CgsArgs {
   const unsigned long long* wflags;
   unsigned long long wepoch;
   int wtile_shift, wnchunks;
+  int early_trigger;             // LGPU_CGS2_EARLY=1: let the next solve's first kernel start (prologue only) during this step
 };
 
 // Device-wide barrier of the consumer threads (pattern of cooperative groups' grid sync): the CTA
@@ -354,6 +355,7 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     } while (v < a.wepoch);
   }
   __syncthreads();
+  if (a.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 8) {
     // ---- producer (one lane).  Local tile i always lives in ring slot i % S, and the passes run
     // over the CTA's tiles in alternating directions (up, down, up): the last S tiles of a pass are
@@ -405,9 +407,10 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) krylov_cgs2_kernel(const __gr
     return;
   }
   // ---- consumers: 64 rows x 4 column groups
-  // (No griddepcontrol.launch_dependents here: letting the next solve's first-stage kernel start while this step is
-  // still running was measured - 0.19 ms per headline step - and made three units in flight on one GPU differ from
-  // the same units solved one after the other in the last bits, profiles/tuning_log_r2.md.)
+  // (griddepcontrol.launch_dependents only behind LGPU_CGS2_EARLY, see the top of the kernel: letting the next solve's
+  // first-stage kernel start while this step is still running is worth 0.15 ms per headline step.  It looked
+  // non-reproducible with three units in flight until the ring releases got their cross-proxy fence
+  // (common.cuh: mbar_release_slot); with the fence 0 of 250 in-flight repetitions differ, profiles/tuning_log_r2.md.)
   // nothing below may precede the kernel before this one - unless w comes with completion flags: then the consumers
   // touch global memory only after the first device-wide barrier, i.e. after every tile of w has been loaded
   if (a.wflags == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1072,6 +1075,8 @@ bool krylov_cgs2_step(const BasisLayout& L, cd* V, int ncols, cd* w, const Krylo
   a.bar_base = *work.gbar_count;
   *work.gbar_count += 2ull * grid;
   a.newcol = newcol; a.vplain = vplain; a.hsub = hsub;
+  static const bool early = [] { const char* e = std::getenv("LGPU_CGS2_EARLY"); return e && e[0] == '1'; }();
+  a.early_trigger = early ? 1 : 0;
   // completion flags only for a context alone on the GPU, with programmatic launches on, one CTA per SM
   static const bool flags_env = [] {
     const char* e = std::getenv("LGPU_CGS2_FLAGS"); const char* p = std::getenv("LGPU_PDL");
