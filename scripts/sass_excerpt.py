@@ -10,13 +10,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "legolas_b200", "liblegolas_b200.so")
 KERNELS = ["slu_fwd_stage_kernel", "slu_bwd_stage_kernel", "slu_upper_kernel", "slu_fused_stage_kernel", "krylov_cgs2_kernelILi9E",
+           "krylov_pass_kernelILb1ELb1E",
            "slu_merge_kernel", "assemble_kernel", "basis_gemm_rows_kernel", "bell_matvec_real_kernelILi6E"]
 PATTERNS = [("UBLKCP", "cp.async.bulk global -> shared (bulk copy engine)"), ("UBLKPF", "cp.async.bulk.prefetch.L2"),
             ("SYNCS", "mbarrier (init / arrive / expect_tx / try_wait)"), ("DFMA", "FP64 FMA"), ("DMMA", "FP64 tensor core"),
             ("SHFL", "warp shuffle"), ("BAR.SYNC", "CTA / named barrier"), ("LDS", "shared-memory load"), ("STS", "shared-memory store"),
             ("LDG", "global load"), ("STG", "global store"), ("LDL", "local-memory load (spill / dynamic index)"),
             ("STL", "local-memory store"), ("ATOM", "global atomic"), ("CCTL", "cache control"), ("ERRBAR", "error barrier"),
-            ("DEPBAR", "dependency barrier"), ("ACQBULK", "bulk acquire"), ("PREEXIT", "griddepcontrol.launch_dependents")]
+            ("DEPBAR", "dependency barrier"), ("ACQBULK", "griddepcontrol.wait"), ("PREEXIT", "griddepcontrol.launch_dependents"),
+            ("FENCE.VIEW.ASYNC", "fence.proxy.async (cross-proxy fence: mbarrier init, ring-slot release)")]
 
 
 def main():
@@ -42,6 +44,13 @@ def main():
             hit = next((i for i in ins if p in i), None)
             if hit:
                 firsts.append(f"    {hit}")
+        # the consumers' release of a ring slot: fence.proxy.async ... plain mbarrier arrival (A1T0), as scheduled
+        rel = next((n for n, i in enumerate(ins) if "SYNCS.ARRIVE" in i and "A1T0" in i), None)
+        if rel is not None:
+            fence = next((n for n in range(rel - 1, max(-1, rel - 40), -1) if "FENCE.VIEW.ASYNC" in ins[n]), None)
+            if fence is not None:
+                firsts.append("    -- release of a ring slot (common.cuh: mbar_release_slot) --")
+                firsts += [f"    {i}" for i in ins[fence:rel + 1] if any(t in i for t in ("FENCE", "WARPSYNC", "SYNCS", "LDS"))]
         if firsts:
             excerpts += [f"`{name}`", "```"] + firsts + ["```", ""]
     out += ["", "Legend: " + "; ".join(f"{p} = {d}" for p, d in PATTERNS), "", "## First occurrences", ""] + excerpts
