@@ -1,8 +1,8 @@
 #!/bin/bash
-# Scratch: three-in-flight vs sequential (scripts/inflight_check.py) under one path switch at a time.
+# Scratch: three-in-flight vs sequential (scripts/inflight/check.py) under one path switch at a time.
 REPS=${1:-250}
 mkdir -p gpurun_out
-run() { name=$1; shift; echo "== $name" ; env "$@" timeout 300 python scripts/inflight_check.py $REPS 2>&1 | grep -v identical | tail -8; }
+run() { name=$1; shift; echo "== $name" ; env "$@" timeout 300 python scripts/inflight/check.py $REPS 2>&1 | grep -v identical | tail -8; }
 {
 run default LGPU_NOP=1
 run pdl0 LGPU_PDL=0

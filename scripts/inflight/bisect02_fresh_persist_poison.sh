@@ -1,7 +1,7 @@
 #!/bin/bash
 REPS=${1:-150}
 mkdir -p gpurun_out
-run() { name=$1; mode=$2; shift 2; echo "== $name" ; env "$@" timeout 300 python scripts/inflight_modes.py $mode $REPS 2>&1 | tail -8; }
+run() { name=$1; mode=$2; shift 2; echo "== $name" ; env "$@" timeout 300 python scripts/inflight/modes.py $mode $REPS 2>&1 | tail -8; }
 {
 run fresh fresh LGPU_NOP=1
 run persist persist LGPU_NOP=1

@@ -1,7 +1,7 @@
 #!/bin/bash
 REPS=${1:-100}
 mkdir -p gpurun_out
-run() { name=$1; shift; echo "== $name"; env LGPU_DBG_DUAL=1 LGPU_DBG_SHARED_PDL=1 "$@" timeout 120 python scripts/inflight_modes.py persist $REPS > gpurun_out/dual_$name.txt 2>&1
+run() { name=$1; shift; echo "== $name"; env LGPU_DBG_DUAL=1 LGPU_DBG_SHARED_PDL=1 "$@" timeout 120 python scripts/inflight/modes.py persist $REPS > gpurun_out/dual_$name.txt 2>&1
   echo "solves with mismatch: $(grep -c 'lgpu dual' gpurun_out/dual_$name.txt)"
   grep "lgpu dual" gpurun_out/dual_$name.txt | sed 's/.*operator \([0-9]*\), step w \([0-9]*\), step h \([0-9]*\).*/op \1 w \2 h \3/' | sort | uniq -c | sort -rn | head -3
   tail -1 gpurun_out/dual_$name.txt; }

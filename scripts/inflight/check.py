@@ -1,7 +1,7 @@
 """Scratch: sequential vs three-in-flight config-5 units, repeated; prints which entries differ and by how much."""
 import sys
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from legolas_b200 import sweep, workloads as wl
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 units = wl.sweep_units(12)

@@ -1,7 +1,7 @@
 """Scratch: headline solve repeated; n_op, hashes of the eigenvalues / vectors and the iteration time of every repetition."""
 import sys, hashlib
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 import legolas_b200 as lb
 from legolas_b200 import equilibria as heq
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 10001

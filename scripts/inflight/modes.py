@@ -1,11 +1,11 @@
 """Scratch: where does the rare in-flight / sequential difference come from?
 mode fresh   : ONE context at a time, a new context for every repetition (allocator history varies, no concurrency)
 mode persist : three contexts in flight, the SAME three contexts for every repetition
-mode inflight: three contexts in flight, new contexts every repetition (scripts/inflight_check.py)
+mode inflight: three contexts in flight, new contexts every repetition (scripts/inflight/check.py)
 """
 import sys
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from legolas_b200 import sweep, workloads as wl
 mode = sys.argv[1]
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 100

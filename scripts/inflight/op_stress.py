@@ -2,7 +2,7 @@
 output of the solve kernels ever change when neighbours run on the GPU?  (argv: repetitions per thread, mode op|solve)"""
 import sys, threading
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from legolas_b200 import api, equilibria, workloads as wl
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 mode = sys.argv[2] if len(sys.argv) > 2 else "op"

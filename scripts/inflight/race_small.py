@@ -1,7 +1,7 @@
 """Scratch for compute-sanitizer racecheck on the round-2 kernels: one config-5 unit on a capped context (the path of
 the in-flight sweeps) and a short headline-type run (G = 1201, nev = 20: programmatic launches, completion flags)."""
 import sys
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 import numpy as np
 import legolas_b200 as lb
 from legolas_b200 import equilibria as heq, workloads as wl

@@ -3,7 +3,7 @@ different NaN pattern before every operator application and Gram-Schmidt step - 
 shared memory it has not written."""
 import sys
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 from legolas_b200 import workloads as wl
 passes = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 units = wl.sweep_units(12)
