@@ -26,11 +26,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // true for exactly one CTA: the last one to arrive; its view of global memory then contains
 // every other CTA's partials.
-__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket, bool wrote_partials) {
   __shared__ bool is_last;
-  __syncthreads();                       // the CTA's partials happen before thread 0's fence ...
+  if (wrote_partials) __threadfence();   // only the threads that published partials need the fence
+  __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();                     // ... which, followed by the ticket, is the release (fence cumulativity)
     const unsigned int t = atomicAdd(ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
@@ -179,7 +179,7 @@ krylov_pass_kernel(BasisLayout L, const cd* __restrict__ V, int ncols, int nstag
     __syncthreads();
     if (tid == 0) partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + KRYLOV_MAXCOL] = cd{red[0] + red[1], 0.0};
   }
-  if (last_block_done(ticket)) {
+  if (last_block_done(ticket, true)) {
     if (DOTS) {
       // one warp per column: lanes stride over the CTA partials, fixed-order shuffle tree
       for (int c = warp; c < ncols; c += PASS_THREADS / 32) {
@@ -853,7 +853,7 @@ vec_axpby_basis_norm_kernel(BasisLayout L, cd a, cd* __restrict__ r, cd b, const
     for (int w = 0; w < 8; ++w) t += red[w];
     partial[static_cast<size_t>(blockIdx.x) * PSTRIDE] = cd{t, 0.0};
   }
-  if (last_block_done(ticket)) {
+  if (last_block_done(ticket, tid == 0)) {
     if (warp == 0) {
       double t = 0.0;
       for (unsigned int bb = lane; bb < gridDim.x; bb += 32) t += partial[static_cast<size_t>(bb) * PSTRIDE].x;
@@ -890,7 +890,7 @@ vec_dot2_kernel(int n, const cd* __restrict__ x, const cd* __restrict__ sv, cons
     for (int w = 0; w < 8; ++w) t += red[tid][w];
     partial[static_cast<size_t>(blockIdx.x) * PSTRIDE + tid] = t;
   }
-  if (last_block_done(ticket)) {
+  if (last_block_done(ticket, tid < 3)) {
     if (warp < 3) {
       cd t{0.0, 0.0};
       for (unsigned int b = lane; b < gridDim.x; b += 32) t += partial[static_cast<size_t>(b) * PSTRIDE + warp];
